@@ -1,0 +1,78 @@
+// Shared helpers for the longspec_b200 CUDA kernels (sm_100a).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/longspec_b200.h"
+
+namespace ls {
+
+void set_error(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return LS_ERR_CUDA;
+    }
+    return LS_OK;
+}
+
+#define LS_REQUIRE(cond, ...)                 \
+    do {                                      \
+        if (!(cond)) {                        \
+            ls::set_error(__VA_ARGS__);       \
+            return LS_ERR_INVALID_ARG;        \
+        }                                     \
+    } while (0)
+
+template <typename T>
+struct Num;
+template <>
+struct Num<__half> {
+    static __device__ __forceinline__ float to_f(__half x) { return __half2float(x); }
+    static __device__ __forceinline__ __half from_f(float x) { return __float2half_rn(x); }
+    static __device__ __forceinline__ uint32_t pack(float a, float b) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    static __device__ __forceinline__ float2 unpack(uint32_t u) {
+        return __half22float2(*reinterpret_cast<__half2*>(&u));
+    }
+};
+template <>
+struct Num<__nv_bfloat16> {
+    static __device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
+    static __device__ __forceinline__ __nv_bfloat16 from_f(float x) { return __float2bfloat16_rn(x); }
+    static __device__ __forceinline__ uint32_t pack(float a, float b) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    static __device__ __forceinline__ float2 unpack(uint32_t u) {
+        return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+    }
+};
+
+// ex2.approx: exact 2^x for the softmax (scores are kept in the log2 domain); -inf -> 0
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace ls
