@@ -262,7 +262,7 @@ class Engine:
         self.descs = []                                # keep ctypes structs alive
 
     # ------------------------------------------------------------------ kernels
-    def _attn(self, q, out, pools, layer, kv_len_ptr, n_q_ptr, q_rows, n_splits, *, kv_len_bias=0, n_tail=0,
+    def _desc(self, q, out, pools, layer, kv_len_ptr, n_q_ptr, q_rows, n_splits, *, kv_len_bias=0, n_tail=0,
               tail_mask=None, window=-1, causal=0, sharded=True):
         d = self.dims
         kvp = pools
@@ -279,9 +279,14 @@ class Engine:
         a.part_offset, a.n_parts_total = sh.rank * n_splits, sh.world * n_splits
         a.kv_shard_begin, a.kv_shard_end, a.tail_owner = sh.begin, sh.end, int(sh.owner)
         a.scale = self.scale
+        return a
+
+    def _attn(self, q, out, pools, layer, kv_len_ptr, n_q_ptr, q_rows, n_splits, **kw):
+        a = self._desc(q, out, pools, layer, kv_len_ptr, n_q_ptr, q_rows, n_splits, **kw)
+        sharded = kw.get("sharded", True)
         self.descs.append(a)
         _lib.call("ls_attn_partial", C.byref(a), _stream())
-        if sh.world > 1:
+        if sharded and self.shard.world > 1:
             self._exchange_partials(a, q_rows)
         _lib.call("ls_attn_combine", C.byref(a), _stream())
         self.launches += 2

@@ -178,6 +178,7 @@ class LlamaGlide:
         host = torch.zeros(4, dtype=torch.int32).pin_memory()
         graph = None
         rounds = 0
+        round_log = []                       # (host time, tokens written) after every round's stop test
         launches0 = eng.launches
         torch.cuda.synchronize()
         start_time = time.time()
@@ -189,6 +190,7 @@ class LlamaGlide:
             host.copy_(st["counters"], non_blocking=True)
             torch.cuda.current_stream().synchronize()
             rounds += 1
+            round_log.append((time.time(), int(host[2])))
             if rounds == 1:
                 self.launches_per_round = eng.launches - launches0
             if host[3] != 0 or sticky_stop:
@@ -202,7 +204,8 @@ class LlamaGlide:
         count = torch.tensor(int(host[0]), device=self.device)
         num = int(host[1])
         self.last_stats = dict(rounds=rounds, launches_per_round=getattr(self, "launches_per_round", 0),
-                               graph=graph is not None)
+                               graph=graph is not None, round_log=round_log, start_time=start_time)
+        self.last_graph = graph
         spec_mask = torch.zeros(1, max_gen_len, dtype=torch.int64, device=self.device)
         return st["output_ids"].clone()[None], count, num, elapsed_time, spec_mask
 

@@ -60,7 +60,7 @@ def verify_mask(tree_mask, acc, gamma):
 ])
 def test_verify_attention_matches_oracle(dtype, H, Hk, n0, shape, acc, splits):
     """kernel (ii): target hybrid tree attention (llama.py:385-421) incl. the KV append layout."""
-    from tests.gpu_util import paged_from_dense, run_attention
+    from gpu_util import paged_from_dense, run_attention
     dev = torch.device("cuda:0")
     tm, offs = random_tree_mask(shape, 5)
     gamma = len(shape)
@@ -92,7 +92,7 @@ def test_verify_attention_matches_oracle(dtype, H, Hk, n0, shape, acc, splits):
 @pytest.mark.parametrize("n0,M,acc_style", [(1500, 16, False), (700, 4, False), (300, 6, True), (40, 3, True), (513, 5, True)])
 def test_draft_self_attention_matches_oracle(dtype, n0, M, acc_style):
     """kernel (i) attention part: window-512 prefix (+ tree tail) (llama_glide.py:261-262,300-329)."""
-    from tests.gpu_util import paged_from_dense, run_attention
+    from gpu_util import paged_from_dense, run_attention
     dev = torch.device("cuda:0")
     H, Hk = 8, 2
     q = gen((M, H, 128), 11, dtype)
@@ -129,7 +129,7 @@ def test_draft_self_attention_matches_oracle(dtype, n0, M, acc_style):
 @pytest.mark.parametrize("n0,M", [(2049, 16), (130, 6), (64, 1)])
 def test_draft_cross_attention_matches_oracle(causal, n0, M):
     """draft cross attention over the target's last-layer cache (llama_glide.py:265,297)."""
-    from tests.gpu_util import paged_from_dense, run_attention
+    from gpu_util import paged_from_dense, run_attention
     dev = torch.device("cuda:0")
     dtype = torch.bfloat16
     H, Hk = 8, 2
@@ -148,7 +148,7 @@ def test_sequence_sharded_partials_combine_to_the_same_result():
     slots, one combine merges them; must equal the unsharded result."""
     import ctypes as C
     from longspec_b200 import _lib
-    from tests.gpu_util import paged_from_dense, run_attention
+    from gpu_util import paged_from_dense, run_attention
     dev = torch.device("cuda:0")
     dtype = torch.bfloat16
     H, Hk, n0, qv = 8, 2, 1000, 20
@@ -196,7 +196,7 @@ def test_full_size_prefix_uniform_attention_property():
     """Full-size property check (N = 131072, Llama-3-8B GQA-4 verify shape, BASELINE configs[2]): with
     K = 0 every key gets equal weight, so the output must equal the mean of the visible V rows -
     a size-independent identity that needs no O(N) oracle run."""
-    from tests.gpu_util import run_attention
+    from gpu_util import run_attention
     from longspec_b200.engine import PagedKV
     dev = torch.device("cuda:0")
     dtype = torch.bfloat16

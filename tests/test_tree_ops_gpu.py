@@ -32,7 +32,7 @@ def test_tree_accept_matches_reference_fixture(golden_dir):
     """ls_tree_accept vs LlamaGlide.tree_verification (llama_glide.py:1128-1175) outputs."""
     from longspec_b200 import _lib
     from longspec_b200.engine import PagedKV, _ptr, _stream
-    from tests.gpu_util import pack_bits
+    from gpu_util import pack_bits
     z = np.load(os.path.join(golden_dir, "tree_verification.npz"))
     for i in range(int(z["n"])):
         g = lambda k: z[f"c{i}_{k}"]
@@ -154,7 +154,7 @@ def test_argmax_rows_first_index_on_ties():
 def test_pack_mask_matches_host_packing():
     from longspec_b200 import _lib
     from longspec_b200.engine import _ptr, _stream
-    from tests.gpu_util import pack_bits
+    from gpu_util import pack_bits
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(5)
     m = (torch.rand(74, 150, generator=g) > 0.5).long()
