@@ -92,7 +92,7 @@ typedef struct ls_attn_desc {
     int32_t causal;             /* 0/1 */
     int32_t dtype;              /* LS_F16 / LS_BF16 */
     int32_t n_splits;           /* split-KV CTAs per kv head on this GPU (>= 1) */
-    int32_t max_kv_len;         /* upper bound of kv_len + n_tail for this launch (sizes each split) */
+    int32_t n_pages;            /* pages in k_pool / v_pool (extent of the TMA tensor maps) */
     int32_t part_offset;        /* first partial slot this launch writes (sequence-sharded multi-GPU) */
     int32_t n_parts_total;      /* partial slots the combine step reduces over */
     int32_t kv_shard_begin;     /* this GPU owns prefix keys [kv_shard_begin, kv_shard_end) of the */
@@ -105,6 +105,9 @@ typedef struct ls_attn_desc {
 int ls_attn_partial(const ls_attn_desc* d, void* stream);
 /* the general mma.sync data path behind ls_attn_partial (kept callable for cross-checks) */
 int ls_attn_partial_mma(const ls_attn_desc* d, void* stream);
+/* the tcgen05/TMA data path: unmasked full 64-key tiles of the prefix, n_splits_tc splits (window < 0,
+ * <= 384 packed rows); ls_attn_partial pairs it with one mma.sync split for the masked remainder */
+int ls_attn_partial_tc(const ls_attn_desc* d, int32_t n_splits_tc, void* stream);
 /* reduces n_parts_total partial slots and writes `out`; run after the partials of all ranks are
  * in the workspace (single GPU: right after ls_attn_partial) */
 int ls_attn_combine(const ls_attn_desc* d, void* stream);

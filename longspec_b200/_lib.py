@@ -24,7 +24,7 @@ class AttnDesc(C.Structure):
         ("q", vp), ("out", vp), ("k_pool", vp), ("v_pool", vp), ("page_table", vp), ("kv_len_ptr", vp),
         ("n_q_ptr", vp), ("tail_mask", vp), ("part_o", vp), ("part_lse", vp),
         ("kv_len_bias", i32), ("q_rows", i32), ("n_heads", i32), ("n_kv_heads", i32), ("n_tail", i32),
-        ("window", i32), ("causal", i32), ("dtype", i32), ("n_splits", i32), ("max_kv_len", i32),
+        ("window", i32), ("causal", i32), ("dtype", i32), ("n_splits", i32), ("n_pages", i32),
         ("part_offset", i32), ("n_parts_total", i32), ("kv_shard_begin", i32), ("kv_shard_end", i32),
         ("tail_owner", i32), ("scale", f32),
     ]
@@ -47,6 +47,7 @@ _SIGS = {
     "ls_sm_count": (i32, []),
     "ls_attn_partial": (i32, [C.POINTER(AttnDesc), vp]),
     "ls_attn_partial_mma": (i32, [C.POINTER(AttnDesc), vp]),
+    "ls_attn_partial_tc": (i32, [C.POINTER(AttnDesc), i32, vp]),
     "ls_attn_combine": (i32, [C.POINTER(AttnDesc), vp]),
     "ls_rope_append": (i32, [vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, i32, i32, i32, vp]),
     "ls_round_begin": (i32, [C.POINTER(TreeState), vp]),

@@ -1,5 +1,7 @@
 // Library-level entry points: version, error string, device query, kernel dispatch.
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -24,4 +26,25 @@ extern "C" int ls_sm_count(void) {
     return n;
 }
 
-extern "C" int ls_attn_partial(const ls_attn_desc* d, void* stream) { return ls_attn_partial_mma(d, stream); }
+extern "C" int ls_attn_partial_mma_remainder(const ls_attn_desc* d, void* stream);
+extern "C" int ls_attn_partial_tc(const ls_attn_desc* d, int n_splits_tc, void* stream);
+
+// Dispatch: unwindowed calls with <= 384 packed rows run the long unmasked prefix on the tcgen05/TMA kernel
+// (n_splits - 1 splits) and the masked remainder on one mma.sync split; everything else (the draft's
+// 512-token window) stays on the general mma.sync kernel.  LONGSPEC_ATTN=mma forces the general path.
+extern "C" int ls_attn_partial(const ls_attn_desc* d, void* stream) {
+    static const int force_mma = []() {
+        const char* e = getenv("LONGSPEC_ATTN");
+        return e && strcmp(e, "mma") == 0;
+    }();
+    if (!d || d->n_kv_heads < 1) return ls_attn_partial_mma(d, stream);
+    const int G = d->n_heads / d->n_kv_heads;
+    const bool tc_ok = !force_mma && d->window < 0 && d->q_rows * G <= 384 && d->n_splits >= 2 && d->n_pages > 0;
+    if (!tc_ok) return ls_attn_partial_mma(d, stream);
+    int rc = ls_attn_partial_tc(d, d->n_splits - 1, stream);
+    if (rc) return rc;
+    ls_attn_desc r = *d;
+    r.n_splits = 1;
+    r.part_offset = d->part_offset + d->n_splits - 1;
+    return ls_attn_partial_mma_remainder(&r, stream);
+}

@@ -75,7 +75,7 @@ struct TilePlan {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(kWarps * 32, 1) attn_partial_kernel(const ls_attn_desc d) {
+__global__ void __launch_bounds__(kWarps * 32, 1) attn_partial_kernel(const ls_attn_desc d, const int remainder) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int split = blockIdx.x, kvh = blockIdx.y, rb = blockIdx.z;
@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) attn_partial_kernel(const ls_a
     const int loc_end = max(min(kv_len, se) - sb, 0);                 // local prefix end
     int loc_beg = 0;
     if (d.window >= 0) loc_beg = min(max(kv_len - n_q - d.window - sb, 0), loc_end);
+    if (remainder) loc_beg = min(tc_full_tiles(d, kv_len, n_q) * kBN, loc_end);   // the rest is on the tcgen05 kernel
     TilePlan tp;
     {
         const int tb = loc_beg / kBN, te = (loc_end + kBN - 1) / kBN;
@@ -389,7 +390,7 @@ static int validate(const ls_attn_desc* d) {
 
 }  // namespace ls
 
-extern "C" int ls_attn_partial_mma(const ls_attn_desc* d, void* stream) {
+static int launch_partial_mma(const ls_attn_desc* d, int remainder, void* stream) {
     using namespace ls;
     int rc = validate(d);
     if (rc != LS_OK) return rc;
@@ -403,11 +404,15 @@ extern "C" int ls_attn_partial_mma(const ls_attn_desc* d, void* stream) {
         attr_set = true;
     }
     if (d->dtype == LS_F16)
-        attn_partial_kernel<__half><<<grid, kWarps * 32, kSmemBytes, st>>>(*d);
+        attn_partial_kernel<__half><<<grid, kWarps * 32, kSmemBytes, st>>>(*d, remainder);
     else
-        attn_partial_kernel<__nv_bfloat16><<<grid, kWarps * 32, kSmemBytes, st>>>(*d);
+        attn_partial_kernel<__nv_bfloat16><<<grid, kWarps * 32, kSmemBytes, st>>>(*d, remainder);
     return check_launch("ls_attn_partial");
 }
+
+extern "C" int ls_attn_partial_mma(const ls_attn_desc* d, void* stream) { return launch_partial_mma(d, 0, stream); }
+// masked remainder behind the tcgen05 kernel: last partial prefix tile, causal rows, tree-masked tail
+extern "C" int ls_attn_partial_mma_remainder(const ls_attn_desc* d, void* stream) { return launch_partial_mma(d, 1, stream); }
 
 extern "C" int ls_attn_combine(const ls_attn_desc* d, void* stream) {
     using namespace ls;

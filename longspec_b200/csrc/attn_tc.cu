@@ -1,0 +1,451 @@
+// tcgen05 / TMA / TMEM split-KV attention over the long, unmasked part of the paged prefix.
+//
+// One CTA = (split, kv head) and ALL packed query rows of that kv head (up to 3 tiles of 128 rows,
+// r = token * G + head-in-group), so every K/V byte is pulled from HBM once per kv head and reused by the
+// whole GQA group and the whole candidate tree from shared memory.
+//
+//   warp 0  (1 thread)  TMA producer: 64-key K and V tiles (2 x [64 x 128B] boxes each, SWIZZLE_128B) from
+//                       the paged pool into a 3-stage shared-memory ring, completion on mbarriers
+//   warp 1  (1 thread)  MMA issuer: S = Q K^T (M128 N64 K16 x8, A = Q tile in smem, B = K tile, both
+//                       K-major) into a double-buffered TMEM accumulator; O_r += P V (M128 N128 K16 x4,
+//                       A = P tile in smem, B = V tile MN-major) into per-row-tile TMEM accumulators
+//   warp 2              TMEM allocation (512 columns: 2 x 64 for S, 3 x 128 for O)
+//   warps 4-7 / 8-11    two softmax warpgroups, alternating steps: tcgen05.ld the S tile (one row per
+//                       thread), online softmax in the log2 domain with lazy rescaling (O in TMEM is only
+//                       rescaled when a row maximum grows by more than 2^8), P rounded to dtype and written
+//                       to swizzled shared memory for the PV MMA
+// The epilogue writes normalised partial O (fp32) and the natural-log LSE per (split, kv head, row); the
+// shared combine kernel (attn_mma.cu) merges them with the partials of the masked remainder (last partial
+// tile, causal rows, tree-masked tail), which stays on the general mma.sync path.
+//
+// Reference semantics: flash_attn_with_kvcache(q, K_Cache, V_Cache, cache_seqlens=cache_lens,
+// return_softmax_lse=True) of llama.py:385 and llama_glide.py:297, restated in oracle/flash_ref.py.
+#include <cuda.h>
+#include <limits.h>
+
+#include <mutex>
+#include <type_traits>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace ls {
+namespace tc {
+
+constexpr int BN = 64;
+constexpr int NR_MAX = 3;
+constexpr int STAGES = 3;
+constexpr int THREADS = 384;
+constexpr int Q_TILE_BYTES = 128 * 256;            // 32 KB: two [128 x 128B] K-chunks
+constexpr int KV_STAGE_BYTES = 4 * 8192;           // K c0 | K c1 | V c0 | V c1
+constexpr int P_BYTES = 128 * 128;                 // 16 KB
+constexpr int OFF_Q = 0;
+constexpr int OFF_KV = OFF_Q + NR_MAX * Q_TILE_BYTES;
+constexpr int OFF_P = OFF_KV + STAGES * KV_STAGE_BYTES;
+constexpr int OFF_STATE = OFF_P + P_BYTES;         // m_ref[384], l[384]
+constexpr int OFF_BAR = OFF_STATE + 2 * NR_MAX * 128 * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
+
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t COL_S = 0;                      // 2 x 64
+constexpr uint32_t COL_O = 128;                    // 3 x 128
+
+// barrier indices
+enum { B_KV_FULL = 0, B_KV_EMPTY = 3, B_S_FULL = 6, B_S_FREE = 8, B_P_FULL = 10, B_P_FREE = 11, B_PV_DONE = 12, B_ALL_DONE = 15, B_COUNT = 16 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// shared-memory matrix descriptor, SWIZZLE_128B, descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
+           (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int fmt, int a_mn, int b_mn) {
+    return (1u << 4) | (static_cast<uint32_t>(fmt) << 7) | (static_cast<uint32_t>(fmt) << 10) |
+           (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16) |
+           (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+#define LS_TMEM_LD32(taddr, v)                                                                                       \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"      \
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                            \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),     \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),            \
+                   "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),          \
+                   "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),          \
+                   "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                              \
+                 : "r"(taddr))
+#define LS_TMEM_ST32(taddr, v)                                                                                       \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"   \
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"                               \
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),           \
+                   "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),        \
+                   "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),     \
+                   "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),     \
+                   "r"(v[31])                                                                                         \
+                 : "memory")
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <typename T>
+__global__ void __launch_bounds__(THREADS, 1)
+attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+               int n_splits_tc) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int split = blockIdx.x, kvh = blockIdx.y;
+    const int G = d.n_heads / d.n_kv_heads;
+    const int n_q = min(*d.n_q_ptr, d.q_rows);
+    const int R = n_q * G;
+    const int NR = (R + 127) / 128;                         // row tiles in use (1..3)
+    const int kv_len = *d.kv_len_ptr + d.kv_len_bias;
+    const int total_tiles = tc_full_tiles(d, kv_len, n_q);
+    const int per = (total_tiles + n_splits_tc - 1) / n_splits_tc;
+    const int tile0 = min(split * per, total_tiles);
+    const int n_tiles = min(tile0 + per, total_tiles) - tile0;
+    const int n_steps = n_tiles * NR;
+
+    float* st_m = reinterpret_cast<float*>(smem + OFF_STATE);
+    float* st_l = st_m + NR_MAX * 128;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + B_COUNT * 8);
+    const uint32_t bar0 = sbase + OFF_BAR;
+    auto bar = [&](int i) { return bar0 + i * 8; };
+
+    // ---- one-time setup ----------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(bar(B_KV_FULL + i), 1); mbar_init(bar(B_KV_EMPTY + i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar(B_S_FULL + i), 1); mbar_init(bar(B_S_FREE + i), 128); }
+        mbar_init(bar(B_P_FULL), 128);
+        mbar_init(bar(B_P_FREE), 1);
+        for (int i = 0; i < NR_MAX; ++i) mbar_init(bar(B_PV_DONE + i), 1);
+        mbar_init(bar(B_ALL_DONE), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int i = tid; i < NR_MAX * 128; i += THREADS) { st_m[i] = -INFINITY; st_l[i] = 0.f; }
+    // Q tiles -> swizzled shared memory (K-major, SWIZZLE_128B): [tile][k-chunk][row][128B]
+    {
+        const T* __restrict__ q = reinterpret_cast<const T*>(d.q);
+        for (int idx = tid; idx < NR * 128 * 16; idx += THREADS) {
+            const int rp = idx >> 4, chunk = idx & 15;
+            const int tile = rp >> 7, row = rp & 127;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (rp < R) {
+                const int i = rp / G, g = rp - i * G;
+                val = *reinterpret_cast<const uint4*>(q + (static_cast<size_t>(i) * d.n_heads + kvh * G + g) * 128 + chunk * 8);
+            }
+            uint8_t* dst = smem + OFF_Q + tile * Q_TILE_BYTES + (chunk >> 3) * 16384 + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = val;
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    constexpr int FMT = sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+    constexpr uint32_t IDESC_QK = make_idesc(128, BN, FMT, 0, 0);
+    constexpr uint32_t IDESC_PV = make_idesc(128, 128, FMT, 0, 1);
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            for (int j = 0; j < n_tiles; ++j) {
+                const int s = j % STAGES;
+                mbar_wait(bar(B_KV_EMPTY + s), ((j / STAGES) & 1) ^ 1);
+                const int tile = tile0 + j;
+                const int page = __ldg(d.page_table + (tile >> 1));
+                const int row = (page * d.n_kv_heads + kvh) * LS_PAGE + (tile & 1) * BN;
+                const uint32_t dst = sbase + OFF_KV + s * KV_STAGE_BYTES;
+                mbar_expect_tx(bar(B_KV_FULL + s), KV_STAGE_BYTES);
+                tma_load_2d(dst, &map_k, 0, row, bar(B_KV_FULL + s));
+                tma_load_2d(dst + 8192, &map_k, 64, row, bar(B_KV_FULL + s));
+                tma_load_2d(dst + 16384, &map_v, 0, row, bar(B_KV_FULL + s));
+                tma_load_2d(dst + 24576, &map_v, 64, row, bar(B_KV_FULL + s));
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            auto issue_pv = [&](int t) {
+                const int j = t / NR, r = t - j * NR, s = j % STAGES;
+                mbar_wait(bar(B_P_FULL), t & 1);
+                tc_fence_after();
+                const uint32_t pa = sbase + OFF_P, vb = sbase + OFF_KV + s * KV_STAGE_BYTES + 16384;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    tc_mma(tmem + COL_O + r * 128, smem_desc(pa + kk * 32, 16, 1024), smem_desc(vb + kk * 2048, 8192, 1024),
+                           IDESC_PV, (j > 0 || kk > 0) ? 1u : 0u);
+                tc_commit(bar(B_P_FREE));
+                tc_commit(bar(B_PV_DONE + r));
+                if (r == NR - 1) tc_commit(bar(B_KV_EMPTY + s));
+            };
+            for (int t = 0; t < n_steps; ++t) {
+                const int j = t / NR, r = t - j * NR, s = j % STAGES, b = t & 1;
+                if (r == 0) mbar_wait(bar(B_KV_FULL + s), (j / STAGES) & 1);
+                mbar_wait(bar(B_S_FREE + b), ((t >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t qa = sbase + OFF_Q + r * Q_TILE_BYTES, kb = sbase + OFF_KV + s * KV_STAGE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    tc_mma(tmem + COL_S + b * BN, smem_desc(qa + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                           smem_desc(kb + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024), IDESC_QK, kk > 0 ? 1u : 0u);
+                tc_commit(bar(B_S_FULL + b));
+                if (t > 0) issue_pv(t - 1);
+            }
+            if (n_steps > 0) {
+                issue_pv(n_steps - 1);
+                tc_commit(bar(B_ALL_DONE));      // every MMA of this CTA has completed once this fires
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= softmax warpgroups =================
+        const int wg = (warp - 4) >> 2;
+        const int quad = warp & 3;                                   // TMEM lane quarter of this warp
+        const int row = quad * 32 + lane;                            // row inside a 128-row tile
+        const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+        const float c2 = d.scale * 1.4426950408889634f;
+        for (int t = wg; t < n_steps; t += 2) {
+            const int j = t / NR, r = t - j * NR, b = t & 1;
+            const bool warp_valid = r * 128 + quad * 32 < R;         // warp-uniform: any valid row in this warp
+            if (!warp_valid) {
+                // padding rows only: keep the barrier protocol, skip the math (their O rows are never read)
+                mbar_wait(bar(B_S_FULL + b), (t >> 1) & 1);
+                mbar_arrive(bar(B_S_FREE + b));
+                mbar_wait(bar(B_P_FREE), (t & 1) ^ 1);
+                mbar_arrive(bar(B_P_FULL));
+                continue;
+            }
+            mbar_wait(bar(B_S_FULL + b), (t >> 1) & 1);
+            tc_fence_after();
+            uint32_t sv[64];
+            LS_TMEM_LD32(lane_addr + COL_S + b * BN, sv);
+            LS_TMEM_LD32(lane_addr + COL_S + b * BN + 32, (sv + 32));
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(bar(B_S_FREE + b));
+            float mx = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 64; ++e) mx = fmaxf(mx, __uint_as_float(sv[e]));
+            mx *= c2;
+            // the row state was written by the other warpgroup at step t - NR; for NR >= 2 the MMA issue order
+            // already orders that write before S_FULL(t), for NR == 1 wait for softmax(t-1) explicitly
+            if (NR == 1 && t > 0) mbar_wait(bar(B_P_FULL), (t - 1) & 1);
+            float m_ref = st_m[r * 128 + row], l = st_l[r * 128 + row];
+            const bool need = mx > m_ref + 8.0f;                     // lazy rescale threshold (2^8)
+            if (__any_sync(0xffffffffu, need)) {
+                const float m_new = need ? mx : m_ref;
+                const float alpha = fast_exp2(m_ref - m_new);        // -inf - x -> 0 on the first tile
+                l *= alpha;
+                m_ref = m_new;
+                if (j > 0) {
+                    // O_r is quiescent once PV(r, j-1) completed
+                    mbar_wait(bar(B_PV_DONE + r), (j - 1) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t ov[32];
+                        LS_TMEM_LD32(lane_addr + COL_O + r * 128 + c * 32, ov);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+                        LS_TMEM_ST32(lane_addr + COL_O + r * 128 + c * 32, ov);
+                    }
+                    tmem_wait_st();
+                    tc_fence_before();
+                }
+            }
+            uint32_t pk[32];
+            float sum = 0.f;
+#pragma unroll
+            for (int e = 0; e < 64; e += 2) {
+                const float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), c2, -m_ref));
+                const float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), c2, -m_ref));
+                sum += p0 + p1;
+                pk[e >> 1] = Num<T>::pack(p0, p1);
+            }
+            l += sum;
+            st_m[r * 128 + row] = m_ref;
+            st_l[r * 128 + row] = l;
+            // P tile -> swizzled smem (A operand of the PV MMA); single buffer: PV(t-1) must be done with it
+            mbar_wait(bar(B_P_FREE), (t & 1) ^ 1);
+            uint8_t* prow = smem + OFF_P + row * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            fence_async_smem();
+            mbar_arrive(bar(B_P_FULL));
+        }
+        // ================= epilogue: normalised partial O + LSE =================
+        const int Rtot = d.q_rows * G;
+        const int part = d.part_offset + split;
+        for (int r = wg; r < NR; r += 2) {
+            const int rp = r * 128 + row;
+            if (n_tiles > 0) {
+                // a dedicated single-phase barrier: PV_DONE[r] may lag by more than one phase here, and a
+                // parity wait would alias
+                mbar_wait(bar(B_ALL_DONE), 0);
+                tc_fence_after();
+            }
+            const float l = st_l[rp], m_ref = st_m[rp];
+            const float inv = (n_tiles > 0 && l > 0.f) ? 1.f / l : 0.f;
+            const size_t base = (static_cast<size_t>(part) * d.n_kv_heads + kvh) * Rtot + rp;
+            if (rp < R) d.part_lse[base] = inv > 0.f ? (m_ref + log2f(l)) * 0.6931471805599453f : -INFINITY;
+            if (r * 128 + quad * 32 < R) {               // warp-uniform (tcgen05.ld is warp-collective)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t ov[32];
+                    if (n_tiles > 0) {
+                        LS_TMEM_LD32(lane_addr + COL_O + r * 128 + c * 32, ov);
+                        tmem_wait_ld();
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) ov[e] = 0u;
+                    }
+                    if (rp < R) {
+                        float* po = d.part_o + base * 128 + c * 32;
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4)
+                            *reinterpret_cast<float4*>(po + e) =
+                                make_float4(__uint_as_float(ov[e]) * inv, __uint_as_float(ov[e + 1]) * inv,
+                                            __uint_as_float(ov[e + 2]) * inv, __uint_as_float(ov[e + 3]) * inv);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+    }
+}
+
+// ---- host side: tensor maps (cached per pool) -----------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr; long long rows; int dtype;
+    bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && dtype == o.dtype; }
+};
+struct MapHash {
+    size_t operator()(const MapKey& k) const { return std::hash<const void*>()(k.ptr) ^ (std::hash<long long>()(k.rows) << 1) ^ k.dtype; }
+};
+
+static int get_map(const void* pool, long long rows, int dtype, CUtensorMap* out) {
+    static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
+    MapKey key{pool, rows, dtype};
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return LS_OK; }
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return LS_ERR_CUDA; }
+    CUtensorMap m;
+    cuuint64_t gdim[2] = {128, static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {256};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult rc = fn(&m, dtype == LS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                     const_cast<void*>(pool), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", static_cast<int>(rc)); return LS_ERR_CUDA; }
+    cache[key] = m;
+    *out = m;
+    return LS_OK;
+}
+
+}  // namespace tc
+}  // namespace ls
+
+// Launch the tensor-core kernel over the unmasked full tiles with `n_splits_tc` splits writing partial slots
+// [part_offset, part_offset + n_splits_tc).  Eligibility is checked by the dispatcher in api.cu.
+extern "C" int ls_attn_partial_tc(const ls_attn_desc* d, int n_splits_tc, void* stream) {
+    using namespace ls;
+    using namespace ls::tc;
+    LS_REQUIRE(d && n_splits_tc >= 1, "ls_attn_partial_tc: bad arguments");
+    const int G = d->n_heads / d->n_kv_heads;
+    LS_REQUIRE(d->q_rows * G <= NR_MAX * 128, "ls_attn_partial_tc: %d packed rows exceed %d", d->q_rows * G, NR_MAX * 128);
+    LS_REQUIRE(d->window < 0, "ls_attn_partial_tc: windowed attention stays on the general path");
+    LS_REQUIRE(d->n_pages > 0, "ls_attn_partial_tc: n_pages must be set");
+    CUtensorMap mk, mv;
+    const long long rows = static_cast<long long>(d->n_pages) * d->n_kv_heads * LS_PAGE;
+    int rc = get_map(d->k_pool, rows, d->dtype, &mk);
+    if (rc) return rc;
+    rc = get_map(d->v_pool, rows, d->dtype, &mv);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(attn_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaFuncSetAttribute(attn_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        attr_set = true;
+    }
+    dim3 grid(n_splits_tc, d->n_kv_heads);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d->dtype == LS_F16)
+        attn_tc_kernel<__half><<<grid, THREADS, SMEM_BYTES, st>>>(*d, mk, mv, n_splits_tc);
+    else
+        attn_tc_kernel<__nv_bfloat16><<<grid, THREADS, SMEM_BYTES, st>>>(*d, mk, mv, n_splits_tc);
+    return check_launch("ls_attn_partial_tc");
+}

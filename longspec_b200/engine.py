@@ -275,7 +275,7 @@ class Engine:
         a.part_o, a.part_lse = _ptr(self.part_o), _ptr(self.part_lse)
         a.kv_len_bias, a.q_rows, a.n_heads, a.n_kv_heads = kv_len_bias, q_rows, d.heads, d.kv_heads
         a.n_tail, a.window, a.causal, a.dtype = n_tail, window, causal, self.code
-        a.n_splits, a.max_kv_len = n_splits, kvp.max_tokens
+        a.n_splits, a.n_pages = n_splits, kvp.n_pages
         a.part_offset, a.n_parts_total = sh.rank * n_splits, sh.world * n_splits
         a.kv_shard_begin, a.kv_shard_end, a.tail_owner = sh.begin, sh.end, int(sh.owner)
         a.scale = self.scale

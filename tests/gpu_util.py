@@ -56,7 +56,7 @@ def run_attention(q, kv, kv_len, n_q, *, n_tail=0, tail_mask=None, window=-1, ca
     a.part_o, a.part_lse = _ptr(part_o), _ptr(part_l)
     a.kv_len_bias, a.q_rows, a.n_heads, a.n_kv_heads = 0, q_rows, H, Hk
     a.n_tail, a.window, a.causal, a.dtype = n_tail, window, causal, _code(dtype)
-    a.n_splits, a.max_kv_len = n_splits, kv.max_tokens
+    a.n_splits, a.n_pages = n_splits, kv.n_pages
     a.part_offset, a.n_parts_total = 0, n_parts
     a.kv_shard_begin, a.kv_shard_end, a.tail_owner = shard
     a.scale = 1.0 / math.sqrt(128)

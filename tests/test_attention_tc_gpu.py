@@ -1,0 +1,86 @@
+"""-m gpu: the tcgen05/TMA attention kernel (ls_attn_partial dispatch) vs the oracle and vs the general
+mma.sync path, staged so that a failure localises the broken piece (plumbing / PV / QK / rescaling)."""
+import pytest
+import torch
+
+from oracle import flash_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def gen(shape, seed, dtype, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype)
+
+
+def run_both(q, K, V, n0, n_q, dtype, splits=4, causal=0):
+    from gpu_util import paged_from_dense, run_attention
+    dev = torch.device("cuda:0")
+    kv = paged_from_dense(K, V, dtype, dev)
+    tc, _, _ = run_attention(q.to(dev), kv, n0, n_q, n_splits=splits, causal=causal, entry="ls_attn_partial")
+    mma, _, _ = run_attention(q.to(dev), kv, n0, n_q, n_splits=splits, causal=causal, entry="ls_attn_partial_mma")
+    return tc.float().cpu(), mma.float().cpu()
+
+
+def test_stage1_constant_v_plumbing():
+    """V == 1 everywhere: any correctly normalised attention returns exactly 1 (pipeline, barriers, epilogue)."""
+    dtype = torch.bfloat16
+    q = gen((74, 8, 128), 1, dtype)
+    K = gen((1000, 2, 128), 2, dtype)
+    V = torch.ones(1000, 2, 128, dtype=dtype)
+    tc, mma = run_both(q, K, V, 900, 74, dtype)
+    torch.testing.assert_close(tc, torch.ones_like(tc), atol=1e-2, rtol=0)
+
+
+def test_stage2_zero_k_checks_pv():
+    """K == 0: uniform weights, output = mean of V (PV MMA, MN-major V descriptor, TMA swizzle)."""
+    dtype = torch.bfloat16
+    q = gen((74, 8, 128), 1, dtype)
+    K = torch.zeros(1100, 2, 128, dtype=dtype)
+    V = gen((1100, 2, 128), 3, dtype)
+    n0 = 1024
+    tc, mma = run_both(q, K, V, n0, 74, dtype)
+    exp = V[:n0].float().mean(0).repeat_interleave(4, dim=0)[None].expand(74, 8, 128)
+    torch.testing.assert_close(mma, exp, atol=5e-3, rtol=0)
+    torch.testing.assert_close(tc, exp, atol=5e-3, rtol=0)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("H,Hk,n0,n_q,splits", [(8, 2, 3000, 74, 5), (32, 8, 16384, 74, 19), (8, 8, 700, 74, 3),
+                                               (10, 2, 5000, 69, 7), (8, 2, 2048, 16, 4), (8, 2, 64, 3, 2), (8, 2, 63, 74, 3)])
+def test_stage3_random_matches_oracle_and_mma(dtype, H, Hk, n0, n_q, splits):
+    q = gen((n_q, H, 128), 1, dtype)
+    K = gen((n0 + 9, Hk, 128), 2, dtype)
+    V = gen((n0 + 9, Hk, 128), 3, dtype)
+    tc, mma = run_both(q, K, V, n0, n_q, dtype, splits)
+    ref, _ = flash_ref.attend(q.float(), K[:n0].float(), V[:n0].float())
+    tol = dict(atol=2e-2, rtol=2e-2) if dtype == torch.bfloat16 else dict(atol=4e-3, rtol=4e-3)
+    torch.testing.assert_close(mma, ref, **tol)
+    torch.testing.assert_close(tc, ref, **tol)
+
+
+def test_stage4_growing_maxima_exercise_lazy_rescale():
+    """Scores that keep growing along the sequence force the O-in-TMEM rescale path many times."""
+    dtype = torch.bfloat16
+    n0 = 4096
+    q = gen((74, 8, 128), 1, dtype)
+    ramp = torch.linspace(0.2, 6.0, n0)[:, None, None]
+    K = (gen((n0, 2, 128), 2, torch.float32) * ramp).to(dtype)
+    V = gen((n0, 2, 128), 3, dtype)
+    tc, mma = run_both(q, K, V, n0, 74, dtype, splits=2)
+    ref, _ = flash_ref.attend(q.float(), K.float(), V.float())
+    torch.testing.assert_close(mma, ref, atol=3e-2, rtol=3e-2)
+    torch.testing.assert_close(tc, ref, atol=3e-2, rtol=3e-2)
+
+
+def test_causal_rows_split_between_tc_and_remainder():
+    """draft cross attention, step 0 (llama_glide.py:265): the causal rows live in the mma remainder."""
+    dtype = torch.bfloat16
+    n0, n_q = 1500, 6
+    q = gen((n_q, 8, 128), 1, dtype)
+    K = gen((n0, 2, 128), 2, dtype)
+    V = gen((n0, 2, 128), 3, dtype)
+    tc, mma = run_both(q, K, V, n0, n_q, dtype, splits=4, causal=1)
+    mask = flash_ref.visible(n_q, n0, True)
+    ref, _ = flash_ref.attend(q.float(), K.float(), V.float(), mask)
+    torch.testing.assert_close(tc, ref, atol=2e-2, rtol=2e-2)
