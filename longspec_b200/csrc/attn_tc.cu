@@ -51,7 +51,10 @@ constexpr uint32_t COL_S = 0;                      // 2 x 64
 constexpr uint32_t COL_O = 128;                    // 3 x 128
 
 // barrier indices
-enum { B_KV_FULL = 0, B_KV_EMPTY = 3, B_S_FULL = 6, B_S_FREE = 8, B_P_FULL = 10, B_P_FREE = 11, B_PV_DONE = 12, B_ALL_DONE = 15, B_COUNT = 16 };
+// P_FULL / P_FREE are indexed by step parity (= softmax warpgroup) although there is a single P buffer: a
+// barrier whose phases alternate between the two warpgroups can be observed two phases behind by a waiter,
+// and mbarrier parity waits alias at that distance.  Per-parity barriers advance one phase per waiter step.
+enum { B_KV_FULL = 0, B_KV_EMPTY = 3, B_S_FULL = 6, B_S_FREE = 8, B_P_FULL = 10, B_P_FREE = 12, B_PV_DONE = 14, B_ALL_DONE = 17, B_COUNT = 18 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -75,6 +78,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "WAIT_DONE:\n\t"
         "}" ::"r"(bar), "r"(parity)
         : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -158,8 +171,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(bar(B_KV_FULL + i), 1); mbar_init(bar(B_KV_EMPTY + i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar(B_S_FULL + i), 1); mbar_init(bar(B_S_FREE + i), 128); }
-        mbar_init(bar(B_P_FULL), 128);
-        mbar_init(bar(B_P_FREE), 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(bar(B_P_FULL + i), 128); mbar_init(bar(B_P_FREE + i), 1); }
         for (int i = 0; i < NR_MAX; ++i) mbar_init(bar(B_PV_DONE + i), 1);
         mbar_init(bar(B_ALL_DONE), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -214,23 +226,20 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            auto issue_pv = [&](int t) {
+            auto issue_pv_ready = [&](int t) {
                 const int j = t / NR, r = t - j * NR, s = j % STAGES;
-                mbar_wait(bar(B_P_FULL), t & 1);
                 tc_fence_after();
                 const uint32_t pa = sbase + OFF_P, vb = sbase + OFF_KV + s * KV_STAGE_BYTES + 16384;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
                     tc_mma(tmem + COL_O + r * 128, smem_desc(pa + kk * 32, 16, 1024), smem_desc(vb + kk * 2048, 8192, 1024),
                            IDESC_PV, (j > 0 || kk > 0) ? 1u : 0u);
-                tc_commit(bar(B_P_FREE));
+                tc_commit(bar(B_P_FREE + (t & 1)));
                 tc_commit(bar(B_PV_DONE + r));
                 if (r == NR - 1) tc_commit(bar(B_KV_EMPTY + s));
             };
-            for (int t = 0; t < n_steps; ++t) {
+            auto issue_qk = [&](int t) {
                 const int j = t / NR, r = t - j * NR, s = j % STAGES, b = t & 1;
-                if (r == 0) mbar_wait(bar(B_KV_FULL + s), (j / STAGES) & 1);
-                mbar_wait(bar(B_S_FREE + b), ((t >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t qa = sbase + OFF_Q + r * Q_TILE_BYTES, kb = sbase + OFF_KV + s * KV_STAGE_BYTES;
 #pragma unroll
@@ -238,12 +247,32 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                     tc_mma(tmem + COL_S + b * BN, smem_desc(qa + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                            smem_desc(kb + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024), IDESC_QK, kk > 0 ? 1u : 0u);
                 tc_commit(bar(B_S_FULL + b));
-                if (t > 0) issue_pv(t - 1);
+            };
+            // Event-driven issue: QK(t) goes out as soon as its S buffer is free (softmax(t-2) has LOADED it) and
+            // its K tile has landed; PV(t) as soon as softmax(t) published P.  Neither waits behind the other, so
+            // the tensor pipe always has the next S tile ready when a softmax warpgroup finishes a step.
+            int tq = 0, tp = 0;
+            bool kv_ready = false;
+            while (tp < n_steps) {
+                bool progressed = false;
+                if (tq < n_steps) {
+                    const int j = tq / NR, r = tq - j * NR, s = j % STAGES, b = tq & 1;
+                    if (r == 0 && !kv_ready) kv_ready = mbar_test(bar(B_KV_FULL + s), (j / STAGES) & 1);
+                    if ((r != 0 || kv_ready) && mbar_test(bar(B_S_FREE + b), ((tq >> 1) & 1) ^ 1)) {
+                        issue_qk(tq);
+                        ++tq;
+                        if (tq % NR == 0) kv_ready = false;
+                        progressed = true;
+                    }
+                }
+                if (tp < tq && mbar_test(bar(B_P_FULL + (tp & 1)), (tp >> 1) & 1)) {
+                    issue_pv_ready(tp);
+                    ++tp;
+                    progressed = true;
+                }
+                if (!progressed) __nanosleep(32);
             }
-            if (n_steps > 0) {
-                issue_pv(n_steps - 1);
-                tc_commit(bar(B_ALL_DONE));      // every MMA of this CTA has completed once this fires
-            }
+            if (n_steps > 0) tc_commit(bar(B_ALL_DONE));         // every MMA of this CTA has completed once this fires
         }
     } else if (warp >= 4) {
         // ================= softmax warpgroups =================
@@ -259,8 +288,8 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                 // padding rows only: keep the barrier protocol, skip the math (their O rows are never read)
                 mbar_wait(bar(B_S_FULL + b), (t >> 1) & 1);
                 mbar_arrive(bar(B_S_FREE + b));
-                mbar_wait(bar(B_P_FREE), (t & 1) ^ 1);
-                mbar_arrive(bar(B_P_FULL));
+                if (t > 0) mbar_wait(bar(B_P_FREE + (b ^ 1)), ((t - 1) >> 1) & 1);
+                mbar_arrive(bar(B_P_FULL + b));
                 continue;
             }
             mbar_wait(bar(B_S_FULL + b), (t >> 1) & 1);
@@ -277,7 +306,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
             mx *= c2;
             // the row state was written by the other warpgroup at step t - NR; for NR >= 2 the MMA issue order
             // already orders that write before S_FULL(t), for NR == 1 wait for softmax(t-1) explicitly
-            if (NR == 1 && t > 0) mbar_wait(bar(B_P_FULL), (t - 1) & 1);
+            if (NR == 1 && t > 0) mbar_wait(bar(B_P_FULL + (b ^ 1)), ((t - 1) >> 1) & 1);
             float m_ref = st_m[r * 128 + row], l = st_l[r * 128 + row];
             const bool need = mx > m_ref + 8.0f;                     // lazy rescale threshold (2^8)
             if (__any_sync(0xffffffffu, need)) {
@@ -315,13 +344,13 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
             st_m[r * 128 + row] = m_ref;
             st_l[r * 128 + row] = l;
             // P tile -> swizzled smem (A operand of the PV MMA); single buffer: PV(t-1) must be done with it
-            mbar_wait(bar(B_P_FREE), (t & 1) ^ 1);
+            if (t > 0) mbar_wait(bar(B_P_FREE + (b ^ 1)), ((t - 1) >> 1) & 1);
             uint8_t* prow = smem + OFF_P + row * 128;
 #pragma unroll
             for (int c = 0; c < 8; ++c)
                 *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
             fence_async_smem();
-            mbar_arrive(bar(B_P_FULL));
+            mbar_arrive(bar(B_P_FULL + b));
         }
         // ================= epilogue: normalised partial O + LSE =================
         const int Rtot = d.q_rows * G;

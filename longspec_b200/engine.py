@@ -246,6 +246,9 @@ class Engine:
         tiles = max((max_local + 63) // 64, 1)
 
         def splits(rows):
+            if rows * G <= 384:
+                # tcgen05 path: one CTA per SM over (split, kv head) + one mma.sync split for the masked remainder
+                return int(max(2, self.sms // d.kv_heads + 1))
             rb = (rows * G + 127) // 128
             return int(max(1, min(tiles, math.ceil(2 * self.sms / (d.kv_heads * rb)), 64)))
         self.n_split_verify = splits(self.q_v)
