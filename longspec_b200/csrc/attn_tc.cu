@@ -109,6 +109,34 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
         "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
+// Lean issue path: descriptors are (lo, hi) register pairs; hi is identical for every operand of this kernel
+// (SBO = 1024 B, descriptor version 1, SWIZZLE_128B), lo = (smem address >> 4) | (LBO >> 4) << 16, so stepping
+// along K is one 32-bit add.  Issued by one elected lane of a fully converged warp (operands stay uniform).
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t LBO_K = (16u >> 4) << 16;         // K-major operands (Q, K, P)
+constexpr uint32_t LBO_V = (8192u >> 4) << 16;       // MN-major V: 64-column chunks are 8 KB apart
+__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
 // shared-memory matrix descriptor, SWIZZLE_128B, descriptor version 1 (sm_100)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
@@ -225,55 +253,67 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            auto issue_pv_ready = [&](int t) {
-                const int j = t / NR, r = t - j * NR, s = j % STAGES;
-                tc_fence_after();
-                const uint32_t pa = sbase + OFF_P, vb = sbase + OFF_KV + s * KV_STAGE_BYTES + 16384;
+        // The whole warp runs this loop converged (all values warp-uniform); one elected lane issues.
+        // Event-driven: QK(t) goes out as soon as its S buffer is free (softmax(t-2) has LOADED it) and its K tile
+        // has landed; PV(t) as soon as softmax(t) published P.  Neither waits behind the other.
+        const uint32_t q_lo = ((sbase + OFF_Q) >> 4) | LBO_K;
+        const uint32_t k_lo = ((sbase + OFF_KV) >> 4) | LBO_K;
+        const uint32_t v_lo = ((sbase + OFF_KV + 16384) >> 4) | LBO_V;
+        const uint32_t p_lo = ((sbase + OFF_P) >> 4) | LBO_K;
+        int tq = 0, rq = 0, sq = 0, phq = 0;          // next QK step: row tile, kv stage, kv_full parity
+        int tp = 0, rp = 0, sp = 0, jp0 = 1;          // next PV step: row tile, kv stage, first-tile flag
+        bool kv_ready = false;
+        while (tp < n_steps) {
+            bool progressed = false;
+            if (tq < n_steps) {
+                const int b = tq & 1;
+                if (rq == 0 && !kv_ready) kv_ready = mbar_test(bar(B_KV_FULL + sq), phq);
+                if ((rq != 0 || kv_ready) && mbar_test(bar(B_S_FREE + b), ((tq >> 1) & 1) ^ 1)) {
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a0 = q_lo + rq * (Q_TILE_BYTES >> 4), b0 = k_lo + sq * (KV_STAGE_BYTES >> 4);
+                        const uint32_t dst = tmem + COL_S + b * BN;
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    tc_mma(tmem + COL_O + r * 128, smem_desc(pa + kk * 32, 16, 1024), smem_desc(vb + kk * 2048, 8192, 1024),
-                           IDESC_PV, (j > 0 || kk > 0) ? 1u : 0u);
-                tc_commit(bar(B_P_FREE + (t & 1)));
-                tc_commit(bar(B_PV_DONE + r));
-                if (r == NR - 1) tc_commit(bar(B_KV_EMPTY + s));
-            };
-            auto issue_qk = [&](int t) {
-                const int j = t / NR, r = t - j * NR, s = j % STAGES, b = t & 1;
-                tc_fence_after();
-                const uint32_t qa = sbase + OFF_Q + r * Q_TILE_BYTES, kb = sbase + OFF_KV + s * KV_STAGE_BYTES;
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk)
-                    tc_mma(tmem + COL_S + b * BN, smem_desc(qa + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                           smem_desc(kb + (kk >> 2) * 8192 + (kk & 3) * 32, 16, 1024), IDESC_QK, kk > 0 ? 1u : 0u);
-                tc_commit(bar(B_S_FULL + b));
-            };
-            // Event-driven issue: QK(t) goes out as soon as its S buffer is free (softmax(t-2) has LOADED it) and
-            // its K tile has landed; PV(t) as soon as softmax(t) published P.  Neither waits behind the other, so
-            // the tensor pipe always has the next S tile ready when a softmax warpgroup finishes a step.
-            int tq = 0, tp = 0;
-            bool kv_ready = false;
-            while (tp < n_steps) {
-                bool progressed = false;
-                if (tq < n_steps) {
-                    const int j = tq / NR, r = tq - j * NR, s = j % STAGES, b = tq & 1;
-                    if (r == 0 && !kv_ready) kv_ready = mbar_test(bar(B_KV_FULL + s), (j / STAGES) & 1);
-                    if ((r != 0 || kv_ready) && mbar_test(bar(B_S_FREE + b), ((tq >> 1) & 1) ^ 1)) {
-                        issue_qk(tq);
-                        ++tq;
-                        if (tq % NR == 0) kv_ready = false;
-                        progressed = true;
+                        for (int kk = 0; kk < 8; ++kk)
+                            tc_mma2(dst, a0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2, b0 + (kk >> 2) * (8192 >> 4) + (kk & 3) * 2,
+                                    IDESC_QK, kk > 0 ? 1u : 0u);
+                        tc_commit(bar(B_S_FULL + b));
                     }
-                }
-                if (tp < tq && mbar_test(bar(B_P_FULL + (tp & 1)), (tp >> 1) & 1)) {
-                    issue_pv_ready(tp);
-                    ++tp;
+                    __syncwarp();
+                    ++tq;
+                    if (++rq == NR) {
+                        rq = 0;
+                        kv_ready = false;
+                        if (++sq == STAGES) { sq = 0; phq ^= 1; }
+                    }
                     progressed = true;
                 }
-                if (!progressed) __nanosleep(32);
             }
-            if (n_steps > 0) tc_commit(bar(B_ALL_DONE));         // every MMA of this CTA has completed once this fires
+            if (tp < tq && mbar_test(bar(B_P_FULL + (tp & 1)), (tp >> 1) & 1)) {
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t b0 = v_lo + sp * (KV_STAGE_BYTES >> 4);
+                    const uint32_t dst = tmem + COL_O + rp * 128;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        tc_mma2(dst, p_lo + kk * 2, b0 + kk * (2048 >> 4), IDESC_PV, (!jp0 || kk > 0) ? 1u : 0u);
+                    tc_commit(bar(B_P_FREE + (tp & 1)));
+                    tc_commit(bar(B_PV_DONE + rp));
+                    if (rp == NR - 1) tc_commit(bar(B_KV_EMPTY + sp));
+                }
+                __syncwarp();
+                ++tp;
+                if (++rp == NR) {
+                    rp = 0;
+                    jp0 = 0;
+                    if (++sp == STAGES) sp = 0;
+                }
+                progressed = true;
+            }
+            if (!progressed) __nanosleep(20);
         }
+        if (n_steps > 0 && elect_one()) tc_commit(bar(B_ALL_DONE));   // every MMA of this CTA has completed once this fires
+        __syncwarp();
     } else if (warp >= 4) {
         // ================= softmax warpgroups =================
         const int wg = (warp - 4) >> 2;
@@ -281,8 +321,10 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         const int row = quad * 32 + lane;                            // row inside a 128-row tile
         const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16);
         const float c2 = d.scale * 1.4426950408889634f;
-        for (int t = wg; t < n_steps; t += 2) {
-            const int j = t / NR, r = t - j * NR, b = t & 1;
+        int j = 0, r = wg;                                            // (key tile, row tile) of step t, kept without divisions
+        for (int t = wg; t < n_steps; t += 2, r += 2) {
+            while (r >= NR) { r -= NR; ++j; }
+            const int b = wg;
             const bool warp_valid = r * 128 + quad * 32 < R;         // warp-uniform: any valid row in this warp
             if (!warp_valid) {
                 // padding rows only: keep the barrier protocol, skip the math (their O rows are never read)
