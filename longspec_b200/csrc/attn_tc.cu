@@ -34,27 +34,47 @@ namespace tc {
 
 constexpr int BN = 64;
 constexpr int NR_MAX = 3;
-constexpr int STAGES = 3;
+constexpr int MAX_STAGES = 4;
 constexpr int THREADS = 384;
-constexpr int Q_TILE_BYTES = 128 * 256;            // 32 KB: two [128 x 128B] K-chunks
-constexpr int KV_STAGE_BYTES = 4 * 8192;           // K c0 | K c1 | V c0 | V c1
-constexpr int P_BYTES = 128 * 128;                 // 16 KB
-constexpr int OFF_Q = 0;
-constexpr int OFF_KV = OFF_Q + NR_MAX * Q_TILE_BYTES;
-constexpr int OFF_P = OFF_KV + STAGES * KV_STAGE_BYTES;
-constexpr int OFF_STATE = OFF_P + P_BYTES;         // m_ref[384], l[384]
-constexpr int OFF_BAR = OFF_STATE + 2 * NR_MAX * 128 * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
+constexpr int KV_STAGE_BYTES = 4 * 8192;           // K c0 | K c1 | V c0 | V c1   (64 keys)
+constexpr int P_BYTES = 128 * 128;                 // one P tile: 128 rows x 64 keys
+constexpr int STATE_BYTES = 3 * NR_MAX * 128 * 4;  // m_ref[384], l[384], version[384]
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = 232448;                 // everything sm_100 allows per CTA (227 KB)
+constexpr int SMEM_USABLE = SMEM_BYTES - 1024;     // minus worst-case 1 KB alignment of the dynamic base
 
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t COL_S = 0;                      // 2 x 64
+constexpr uint32_t COL_S = 0;                      // one 128 x 64 fp32 score tile
+constexpr uint32_t COL_P = 64;                     // two 128 x 64 bf16/fp16 probability tiles (32 columns each)
 constexpr uint32_t COL_O = 128;                    // 3 x 128
 
-// barrier indices
-// P_FULL / P_FREE are indexed by step parity (= softmax warpgroup) although there is a single P buffer: a
-// barrier whose phases alternate between the two warpgroups can be observed two phases behind by a waiter,
-// and mbarrier parity waits alias at that distance.  Per-parity barriers advance one phase per waiter step.
-enum { B_KV_FULL = 0, B_KV_EMPTY = 3, B_S_FULL = 6, B_S_FREE = 8, B_P_FULL = 10, B_P_FREE = 12, B_PV_DONE = 14, B_ALL_DONE = 17, B_COUNT = 18 };
+// Shared-memory plan (all regions 1 KB aligned for SWIZZLE_128B):
+//   Q   row tiles 0,1: [2 k-chunks][128 rows][128 B]; row tile 2 keeps only 64 rows when it has <= 64 valid rows
+//       (the M=128 MMA then reads 64 rows of whatever follows - those S rows belong to padding and are never used)
+//   KV  ring of 2..4 stages of 64-key K and V tiles, as many as fit
+//   (P never touches shared memory: the softmax warpgroups store it to TMEM and the PV MMA reads its A operand
+//    from there - shared-memory bandwidth, 128 B/clk, is the scarce resource of this kernel)
+struct Plan {
+    int q2_rows, q_bytes, stages, off_kv, off_p, off_state, off_bar;
+};
+__host__ __device__ inline Plan make_plan(int R) {
+    Plan p;
+    const int NR = (R + 127) / 128;
+    p.q2_rows = (NR == 3 && R - 256 <= 64) ? 64 : 128;
+    p.q_bytes = NR < 3 ? NR * 32768 : 65536 + p.q2_rows * 256;
+    const int fixed = p.q_bytes + STATE_BYTES + BAR_BYTES;
+    int st = (SMEM_USABLE - fixed) / KV_STAGE_BYTES;
+    p.stages = st > MAX_STAGES ? MAX_STAGES : st;
+    p.off_kv = p.q_bytes;
+    p.off_p = 0;
+    p.off_state = p.off_kv + p.stages * KV_STAGE_BYTES;
+    p.off_bar = p.off_state + STATE_BYTES;
+    return p;
+}
+
+// P_FULL / P_FREE are indexed by step parity (= softmax warpgroup = P buffer).  Every barrier is waited on
+// phase by phase by its waiter, so mbarrier parity waits can never alias.
+enum { B_KV_FULL = 0, B_KV_EMPTY = 4, B_S_FULL = 8, B_S_FREE = 10, B_P_FULL = 12, B_P_FREE = 14, B_PV_DONE = 16, B_ALL_DONE = 19, B_COUNT = 20 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -100,18 +120,9 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-// Lean issue path: descriptors are (lo, hi) register pairs; hi is identical for every operand of this kernel
-// (SBO = 1024 B, descriptor version 1, SWIZZLE_128B), lo = (smem address >> 4) | (LBO >> 4) << 16, so stepping
-// along K is one 32-bit add.  Issued by one elected lane of a fully converged warp (operands stay uniform).
+// Descriptors are (lo, hi) register pairs; hi is identical for every operand of this kernel (SBO = 1024 B,
+// descriptor version 1, SWIZZLE_128B), lo = (smem address >> 4) | (LBO >> 4) << 16, so stepping along K is
+// one 32-bit add.  Issued by one elected lane of a fully converged warp (operands stay in uniform registers).
 constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
 constexpr uint32_t LBO_K = (16u >> 4) << 16;         // K-major operands (Q, K, P)
 constexpr uint32_t LBO_V = (8192u >> 4) << 16;       // MN-major V: 64-column chunks are 8 KB apart
@@ -127,6 +138,18 @@ __device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t
         "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(acc)
         : "memory");
 }
+// A operand from TMEM (the P tile), B from shared memory
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(acc)
+        : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -137,15 +160,27 @@ __device__ __forceinline__ bool elect_one() {
         "}" : "=r"(pred));
     return pred != 0;
 }
-// shared-memory matrix descriptor, SWIZZLE_128B, descriptor version 1 (sm_100)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return static_cast<uint64_t>((addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
-           (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int fmt, int a_mn, int b_mn) {
     return (1u << 4) | (static_cast<uint32_t>(fmt) << 7) | (static_cast<uint32_t>(fmt) << 10) |
            (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16) |
            (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+// packed fp32x2 arithmetic (sm_100): halves the issue slots of the softmax inner loop
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
 }
 
 #define LS_TMEM_LD32(taddr, v)                                                                                       \
@@ -182,6 +217,8 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
     const int n_q = min(*d.n_q_ptr, d.q_rows);
     const int R = n_q * G;
     const int NR = (R + 127) / 128;                         // row tiles in use (1..3)
+    const Plan pl = make_plan(R);
+    const int STAGES = pl.stages;
     const int kv_len = *d.kv_len_ptr + d.kv_len_bias;
     const int total_tiles = tc_full_tiles(d, kv_len, n_q);
     const int per = (total_tiles + n_splits_tc - 1) / n_splits_tc;
@@ -189,15 +226,16 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
     const int n_tiles = min(tile0 + per, total_tiles) - tile0;
     const int n_steps = n_tiles * NR;
 
-    float* st_m = reinterpret_cast<float*>(smem + OFF_STATE);
+    float* st_m = reinterpret_cast<float*>(smem + pl.off_state);
     float* st_l = st_m + NR_MAX * 128;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + B_COUNT * 8);
-    const uint32_t bar0 = sbase + OFF_BAR;
+    uint32_t* st_ver = reinterpret_cast<uint32_t*>(st_l + NR_MAX * 128);   // key tiles already folded into (m, l) of a row
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pl.off_bar + B_COUNT * 8);
+    const uint32_t bar0 = sbase + pl.off_bar;
     auto bar = [&](int i) { return bar0 + i * 8; };
 
     // ---- one-time setup ----------------------------------------------------------------------------
     if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(bar(B_KV_FULL + i), 1); mbar_init(bar(B_KV_EMPTY + i), 1); }
+        for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(bar(B_KV_FULL + i), 1); mbar_init(bar(B_KV_EMPTY + i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar(B_S_FULL + i), 1); mbar_init(bar(B_S_FREE + i), 128); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar(B_P_FULL + i), 128); mbar_init(bar(B_P_FREE + i), 1); }
         for (int i = 0; i < NR_MAX; ++i) mbar_init(bar(B_PV_DONE + i), 1);
@@ -208,19 +246,21 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int i = tid; i < NR_MAX * 128; i += THREADS) { st_m[i] = -INFINITY; st_l[i] = 0.f; }
+    for (int i = tid; i < NR_MAX * 128; i += THREADS) { st_m[i] = -INFINITY; st_l[i] = 0.f; st_ver[i] = 0u; }
     // Q tiles -> swizzled shared memory (K-major, SWIZZLE_128B): [tile][k-chunk][row][128B]
     {
         const T* __restrict__ q = reinterpret_cast<const T*>(d.q);
-        for (int idx = tid; idx < NR * 128 * 16; idx += THREADS) {
+        const int rows_total = NR < 3 ? NR * 128 : 256 + pl.q2_rows;
+        for (int idx = tid; idx < rows_total * 16; idx += THREADS) {
             const int rp = idx >> 4, chunk = idx & 15;
             const int tile = rp >> 7, row = rp & 127;
+            const int chunk_stride = tile < 2 ? 16384 : pl.q2_rows * 128;
             uint4 val = make_uint4(0, 0, 0, 0);
             if (rp < R) {
                 const int i = rp / G, g = rp - i * G;
                 val = *reinterpret_cast<const uint4*>(q + (static_cast<size_t>(i) * d.n_heads + kvh * G + g) * 128 + chunk * 8);
             }
-            uint8_t* dst = smem + OFF_Q + tile * Q_TILE_BYTES + (chunk >> 3) * 16384 + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+            uint8_t* dst = smem + tile * 32768 + (chunk >> 3) * chunk_stride + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
             *reinterpret_cast<uint4*>(dst) = val;
         }
     }
@@ -230,36 +270,38 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    constexpr int FMT = sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+    constexpr int FMT = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
     constexpr uint32_t IDESC_QK = make_idesc(128, BN, FMT, 0, 0);
     constexpr uint32_t IDESC_PV = make_idesc(128, 128, FMT, 0, 1);
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            for (int j = 0; j < n_tiles; ++j) {
-                const int s = j % STAGES;
-                mbar_wait(bar(B_KV_EMPTY + s), ((j / STAGES) & 1) ^ 1);
+        // ================= TMA producer (warp converged, one elected lane issues) =================
+        int s = 0, ph = 0;
+        for (int j = 0; j < n_tiles; ++j) {
+            mbar_wait(bar(B_KV_EMPTY + s), ph ^ 1);
+            if (elect_one()) {
                 const int tile = tile0 + j;
                 const int page = __ldg(d.page_table + (tile >> 1));
                 const int row = (page * d.n_kv_heads + kvh) * LS_PAGE + (tile & 1) * BN;
-                const uint32_t dst = sbase + OFF_KV + s * KV_STAGE_BYTES;
+                const uint32_t dst = sbase + pl.off_kv + s * KV_STAGE_BYTES;
                 mbar_expect_tx(bar(B_KV_FULL + s), KV_STAGE_BYTES);
                 tma_load_2d(dst, &map_k, 0, row, bar(B_KV_FULL + s));
                 tma_load_2d(dst + 8192, &map_k, 64, row, bar(B_KV_FULL + s));
                 tma_load_2d(dst + 16384, &map_v, 0, row, bar(B_KV_FULL + s));
                 tma_load_2d(dst + 24576, &map_v, 64, row, bar(B_KV_FULL + s));
             }
+            __syncwarp();
+            if (++s == STAGES) { s = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         // The whole warp runs this loop converged (all values warp-uniform); one elected lane issues.
         // Event-driven: QK(t) goes out as soon as its S buffer is free (softmax(t-2) has LOADED it) and its K tile
         // has landed; PV(t) as soon as softmax(t) published P.  Neither waits behind the other.
-        const uint32_t q_lo = ((sbase + OFF_Q) >> 4) | LBO_K;
-        const uint32_t k_lo = ((sbase + OFF_KV) >> 4) | LBO_K;
-        const uint32_t v_lo = ((sbase + OFF_KV + 16384) >> 4) | LBO_V;
-        const uint32_t p_lo = ((sbase + OFF_P) >> 4) | LBO_K;
+        const uint32_t q_lo = (sbase >> 4) | LBO_K;
+        const uint32_t k_lo = ((sbase + pl.off_kv) >> 4) | LBO_K;
+        const uint32_t v_lo = ((sbase + pl.off_kv + 16384) >> 4) | LBO_V;
+        const uint32_t q2_chunk = (pl.q2_rows * 128) >> 4;
         int tq = 0, rq = 0, sq = 0, phq = 0;          // next QK step: row tile, kv stage, kv_full parity
         int tp = 0, rp = 0, sp = 0, jp0 = 1;          // next PV step: row tile, kv stage, first-tile flag
         bool kv_ready = false;
@@ -268,14 +310,16 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
             if (tq < n_steps) {
                 const int b = tq & 1;
                 if (rq == 0 && !kv_ready) kv_ready = mbar_test(bar(B_KV_FULL + sq), phq);
-                if ((rq != 0 || kv_ready) && mbar_test(bar(B_S_FREE + b), ((tq >> 1) & 1) ^ 1)) {
+                // single S tile: QK(t) may overwrite it once softmax(t-1) (the other warpgroup) has loaded it
+                if ((rq != 0 || kv_ready) && (tq == 0 || mbar_test(bar(B_S_FREE + (b ^ 1)), ((tq - 1) >> 1) & 1))) {
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t a0 = q_lo + rq * (Q_TILE_BYTES >> 4), b0 = k_lo + sq * (KV_STAGE_BYTES >> 4);
-                        const uint32_t dst = tmem + COL_S + b * BN;
+                        const uint32_t a0 = q_lo + rq * (32768 >> 4), b0 = k_lo + sq * (KV_STAGE_BYTES >> 4);
+                        const uint32_t a_chunk = rq < 2 ? (16384u >> 4) : q2_chunk;
+                        const uint32_t dst = tmem + COL_S;
 #pragma unroll
                         for (int kk = 0; kk < 8; ++kk)
-                            tc_mma2(dst, a0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2, b0 + (kk >> 2) * (8192 >> 4) + (kk & 3) * 2,
+                            tc_mma2(dst, a0 + (kk >> 2) * a_chunk + (kk & 3) * 2, b0 + (kk >> 2) * (8192 >> 4) + (kk & 3) * 2,
                                     IDESC_QK, kk > 0 ? 1u : 0u);
                         tc_commit(bar(B_S_FULL + b));
                     }
@@ -292,11 +336,11 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
             if (tp < tq && mbar_test(bar(B_P_FULL + (tp & 1)), (tp >> 1) & 1)) {
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t b0 = v_lo + sp * (KV_STAGE_BYTES >> 4);
+                    const uint32_t a0 = tmem + COL_P + (tp & 1) * 32, b0 = v_lo + sp * (KV_STAGE_BYTES >> 4);
                     const uint32_t dst = tmem + COL_O + rp * 128;
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        tc_mma2(dst, p_lo + kk * 2, b0 + kk * (2048 >> 4), IDESC_PV, (!jp0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < 4; ++kk)      // 16 keys = 8 packed TMEM columns per K step
+                        tc_mma_ts(dst, a0 + kk * 8, b0 + kk * (2048 >> 4), IDESC_PV, (!jp0 || kk > 0) ? 1u : 0u);
                     tc_commit(bar(B_P_FREE + (tp & 1)));
                     tc_commit(bar(B_PV_DONE + rp));
                     if (rp == NR - 1) tc_commit(bar(B_KV_EMPTY + sp));
@@ -316,39 +360,52 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         __syncwarp();
     } else if (warp >= 4) {
         // ================= softmax warpgroups =================
-        const int wg = (warp - 4) >> 2;
+        const int wg = (warp - 4) >> 2;                              // = step parity = S buffer = P buffer
         const int quad = warp & 3;                                   // TMEM lane quarter of this warp
         const int row = quad * 32 + lane;                            // row inside a 128-row tile
         const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16);
         const float c2 = d.scale * 1.4426950408889634f;
-        int j = 0, r = wg;                                            // (key tile, row tile) of step t, kept without divisions
+        const uint64_t c2x2 = pack2(c2, c2);
+        const int b = wg;
+        int j = 0, r = wg;                                           // (key tile, row tile) of step t, kept without divisions
         for (int t = wg; t < n_steps; t += 2, r += 2) {
             while (r >= NR) { r -= NR; ++j; }
-            const int b = wg;
+            const int u = t >> 1;                                     // use count of this warpgroup's buffers
             const bool warp_valid = r * 128 + quad * 32 < R;         // warp-uniform: any valid row in this warp
             if (!warp_valid) {
                 // padding rows only: keep the barrier protocol, skip the math (their O rows are never read)
-                mbar_wait(bar(B_S_FULL + b), (t >> 1) & 1);
+                mbar_wait(bar(B_S_FULL + b), u & 1);
                 mbar_arrive(bar(B_S_FREE + b));
-                if (t > 0) mbar_wait(bar(B_P_FREE + (b ^ 1)), ((t - 1) >> 1) & 1);
+                mbar_wait(bar(B_P_FREE + b), (u & 1) ^ 1);
                 mbar_arrive(bar(B_P_FULL + b));
                 continue;
             }
-            mbar_wait(bar(B_S_FULL + b), (t >> 1) & 1);
+            mbar_wait(bar(B_S_FULL + b), u & 1);
             tc_fence_after();
             uint32_t sv[64];
-            LS_TMEM_LD32(lane_addr + COL_S + b * BN, sv);
-            LS_TMEM_LD32(lane_addr + COL_S + b * BN + 32, (sv + 32));
+            LS_TMEM_LD32(lane_addr + COL_S, sv);
+            LS_TMEM_LD32(lane_addr + COL_S + 32, (sv + 32));
             tmem_wait_ld();
             tc_fence_before();
             mbar_arrive(bar(B_S_FREE + b));
-            float mx = -INFINITY;
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-            for (int e = 0; e < 64; ++e) mx = fmaxf(mx, __uint_as_float(sv[e]));
-            mx *= c2;
-            // the row state was written by the other warpgroup at step t - NR; for NR >= 2 the MMA issue order
-            // already orders that write before S_FULL(t), for NR == 1 wait for softmax(t-1) explicitly
-            if (NR == 1 && t > 0) mbar_wait(bar(B_P_FULL + (b ^ 1)), ((t - 1) >> 1) & 1);
+            for (int e = 0; e < 64; e += 8) {
+                mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])));
+                mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])));
+                mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sv[e + 4]), __uint_as_float(sv[e + 5])));
+                mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sv[e + 6]), __uint_as_float(sv[e + 7])));
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c2;
+            // The row state of (r, j-1) was written by the OTHER warpgroup when NR is odd.  Hand it over through a
+            // per-row version counter (release/acquire in shared memory): exact, and free of mbarrier aliasing.
+            {
+                const uint32_t va = smem_u32(st_ver + r * 128 + row);
+                uint32_t ver;
+                do {
+                    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(ver) : "r"(va) : "memory");
+                } while (ver != static_cast<uint32_t>(j));
+            }
             float m_ref = st_m[r * 128 + row], l = st_l[r * 128 + row];
             const bool need = mx > m_ref + 8.0f;                     // lazy rescale threshold (2^8)
             if (__any_sync(0xffffffffu, need)) {
@@ -357,7 +414,9 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                 l *= alpha;
                 m_ref = m_new;
                 if (j > 0) {
-                    // O_r is quiescent once PV(r, j-1) completed
+                    // O_r is quiescent once PV(r, j-1) completed.  First make sure PV(t-2) is complete (our own
+                    // P_FREE phase) so that PV_DONE[r] is at most one phase behind and the parity wait cannot alias.
+                    mbar_wait(bar(B_P_FREE + b), (u & 1) ^ 1);
                     mbar_wait(bar(B_PV_DONE + r), (j - 1) & 1);
                     tc_fence_after();
 #pragma unroll
@@ -373,48 +432,58 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                     tc_fence_before();
                 }
             }
+            // p = 2^(s * c2 - m_ref), packed fp32x2 FMA / ADD, four independent partial sums
+            const uint64_t negm = pack2(-m_ref, -m_ref);
+            uint64_t sum_a = 0ull, sum_b = 0ull;                     // {0.f, 0.f}
             uint32_t pk[32];
-            float sum = 0.f;
 #pragma unroll
-            for (int e = 0; e < 64; e += 2) {
-                const float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), c2, -m_ref));
-                const float p1 = fast_exp2(fmaf(__uint_as_float(sv[e + 1]), c2, -m_ref));
-                sum += p0 + p1;
+            for (int e = 0; e < 64; e += 4) {
+                float x0, x1, x2, x3;
+                unpack2(fma2(pack2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), c2x2, negm), x0, x1);
+                unpack2(fma2(pack2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), c2x2, negm), x2, x3);
+                const float p0 = fast_exp2(x0), p1 = fast_exp2(x1), p2 = fast_exp2(x2), p3 = fast_exp2(x3);
+                sum_a = add2(sum_a, pack2(p0, p1));
+                sum_b = add2(sum_b, pack2(p2, p3));
                 pk[e >> 1] = Num<T>::pack(p0, p1);
+                pk[(e >> 1) + 1] = Num<T>::pack(p2, p3);
             }
-            l += sum;
+            {
+                float a0, a1, b0, b1;
+                unpack2(add2(sum_a, sum_b), a0, a1);
+                (void)b0; (void)b1;
+                l += a0 + a1;
+            }
             st_m[r * 128 + row] = m_ref;
             st_l[r * 128 + row] = l;
-            // P tile -> swizzled smem (A operand of the PV MMA); single buffer: PV(t-1) must be done with it
-            if (t > 0) mbar_wait(bar(B_P_FREE + (b ^ 1)), ((t - 1) >> 1) & 1);
-            uint8_t* prow = smem + OFF_P + row * 128;
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-            fence_async_smem();
+            asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(st_ver + r * 128 + row)), "r"(static_cast<uint32_t>(j + 1)) : "memory");
+            // P tile -> this warpgroup's TMEM buffer (A operand of the PV MMA, 2 values per 32-bit column);
+            // PV(t-2) must be done with it
+            mbar_wait(bar(B_P_FREE + b), (u & 1) ^ 1);
+            tc_fence_after();
+            LS_TMEM_ST32(lane_addr + COL_P + b * 32, pk);
+            tmem_wait_st();
+            tc_fence_before();
             mbar_arrive(bar(B_P_FULL + b));
         }
         // ================= epilogue: normalised partial O + LSE =================
         const int Rtot = d.q_rows * G;
         const int part = d.part_offset + split;
-        for (int r = wg; r < NR; r += 2) {
-            const int rp = r * 128 + row;
+        for (int re = wg; re < NR; re += 2) {
+            const int rp = re * 128 + row;
             if (n_tiles > 0) {
-                // a dedicated single-phase barrier: PV_DONE[r] may lag by more than one phase here, and a
-                // parity wait would alias
-                mbar_wait(bar(B_ALL_DONE), 0);
+                mbar_wait(bar(B_ALL_DONE), 0);       // single-phase barrier: no parity aliasing
                 tc_fence_after();
             }
             const float l = st_l[rp], m_ref = st_m[rp];
             const float inv = (n_tiles > 0 && l > 0.f) ? 1.f / l : 0.f;
             const size_t base = (static_cast<size_t>(part) * d.n_kv_heads + kvh) * Rtot + rp;
             if (rp < R) d.part_lse[base] = inv > 0.f ? (m_ref + log2f(l)) * 0.6931471805599453f : -INFINITY;
-            if (r * 128 + quad * 32 < R) {               // warp-uniform (tcgen05.ld is warp-collective)
+            if (re * 128 + quad * 32 < R) {               // warp-uniform (tcgen05.ld is warp-collective)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t ov[32];
                     if (n_tiles > 0) {
-                        LS_TMEM_LD32(lane_addr + COL_O + r * 128 + c * 32, ov);
+                        LS_TMEM_LD32(lane_addr + COL_O + re * 128 + c * 32, ov);
                         tmem_wait_ld();
                     } else {
 #pragma unroll
