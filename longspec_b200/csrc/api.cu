@@ -28,19 +28,25 @@ extern "C" int ls_sm_count(void) {
 
 extern "C" int ls_attn_partial_mma_remainder(const ls_attn_desc* d, void* stream);
 extern "C" int ls_attn_partial_tc(const ls_attn_desc* d, int n_splits_tc, void* stream);
+extern "C" int ls_attn_partial_tc_fused(const ls_attn_desc* d, void* stream);
 
-// Dispatch: unwindowed calls with <= 384 packed rows run the long unmasked prefix on the tcgen05/TMA kernel
-// (n_splits - 1 splits) and the masked remainder on one mma.sync split; everything else (the draft's
-// 512-token window) stays on the general mma.sync kernel.  LONGSPEC_ATTN=mma forces the general path.
+// Dispatch: unwindowed calls with <= 384 packed rows run on the tcgen05/TMA kernel: n_splits - 1 CTAs per kv head
+// stream the long unmasked prefix and one more CTA handles the masked remainder (partial tile, causal rows,
+// tree-masked tail) in the same launch; everything else (the draft's 512-token window) stays on the general
+// mma.sync kernel.  LONGSPEC_ATTN=mma forces the general path, LONGSPEC_ATTN=tc+mma the unfused pair.
 extern "C" int ls_attn_partial(const ls_attn_desc* d, void* stream) {
-    static const int force_mma = []() {
+    static const int mode = []() {
         const char* e = getenv("LONGSPEC_ATTN");
-        return e && strcmp(e, "mma") == 0;
+        if (e && strcmp(e, "mma") == 0) return 1;
+        if (e && strcmp(e, "tc+mma") == 0) return 2;
+        return 0;
     }();
+    const int force_mma = mode == 1;
     if (!d || d->n_kv_heads < 1) return ls_attn_partial_mma(d, stream);
     const int G = d->n_heads / d->n_kv_heads;
-    const bool tc_ok = !force_mma && d->window < 0 && d->q_rows * G <= 384 && d->n_splits >= 2 && d->n_pages > 0;
+    const bool tc_ok = !force_mma && d->window < 0 && d->q_rows * G <= 384 && d->n_pages > 0 && (mode == 0 || d->n_splits >= 2);
     if (!tc_ok) return ls_attn_partial_mma(d, stream);
+    if (mode == 0) return ls_attn_partial_tc_fused(d, stream);
     int rc = ls_attn_partial_tc(d, d->n_splits - 1, stream);
     if (rc) return rc;
     ls_attn_desc r = *d;

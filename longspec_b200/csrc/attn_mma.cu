@@ -332,9 +332,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) attn_partial_kernel(const ls_a
     }
 }
 
-// One warp per (packed row, kv head): merge n_parts_total partials, write `out` in dtype.
+// One warp per (packed row, kv head): merge n_parts_total partials, write `out` in dtype.  The LSEs of up to 32
+// parts are held one per lane, weights are broadcast by shuffle and the 512-byte partial rows are fetched with
+// independent 16-byte loads (4 in flight per lane), so the merge is bandwidth- rather than latency-bound.
 template <typename T>
-__global__ void __launch_bounds__(128) attn_combine_kernel(const ls_attn_desc d) {
+__global__ void __launch_bounds__(256) attn_combine_kernel(const ls_attn_desc d) {
     const int G = d.n_heads / d.n_kv_heads;
     const int Rtot = d.q_rows * G;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -346,21 +348,30 @@ __global__ void __launch_bounds__(128) attn_combine_kernel(const ls_attn_desc d)
     T* out = reinterpret_cast<T*>(d.out) + (static_cast<size_t>(i) * d.n_heads + kvh * G + g) * kD + lane * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < n_q) {
+        const size_t stride = static_cast<size_t>(d.n_kv_heads) * Rtot;        // between parts, in rows
+        const size_t row0 = static_cast<size_t>(kvh) * Rtot + r;
+        const int P = d.n_parts_total;
         float mx = -INFINITY;
-        for (int p = lane; p < d.n_parts_total; p += 32)
-            mx = fmaxf(mx, d.part_lse[(static_cast<size_t>(p) * d.n_kv_heads + kvh) * Rtot + r]);
+        for (int p = lane; p < P; p += 32) mx = fmaxf(mx, d.part_lse[p * stride + row0]);
         mx = warp_max(mx);
         float wsum = 0.f;
         if (mx != -INFINITY) {
-            for (int p = 0; p < d.n_parts_total; ++p) {
-                const size_t base = (static_cast<size_t>(p) * d.n_kv_heads + kvh) * Rtot + r;
-                const float lse = d.part_lse[base];
-                if (lse == -INFINITY) continue;
-                const float w = __expf(lse - mx);
-                const float4 v = *reinterpret_cast<const float4*>(d.part_o + base * kD + lane * 4);
-                acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
-                wsum += w;
+            for (int p0 = 0; p0 < P; p0 += 32) {
+                const int p = p0 + lane;
+                const float lse = p < P ? d.part_lse[p * stride + row0] : -INFINITY;
+                const float w_mine = lse == -INFINITY ? 0.f : __expf(lse - mx);
+                wsum += w_mine;
+                const int cnt = min(32, P - p0);
+                const float* base = d.part_o + (p0 * stride + row0) * kD + lane * 4;
+#pragma unroll 4
+                for (int k = 0; k < cnt; ++k) {
+                    const float w = __shfl_sync(0xffffffffu, w_mine, k);
+                    const float4 v = *reinterpret_cast<const float4*>(base + k * stride * kD);
+                    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                    acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                }
             }
+            wsum = warp_sum(wsum);
             const float inv = 1.f / wsum;
             acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
         }
@@ -420,11 +431,11 @@ extern "C" int ls_attn_combine(const ls_attn_desc* d, void* stream) {
     if (rc != LS_OK) return rc;
     const int G = d->n_heads / d->n_kv_heads;
     const int warps = d->q_rows * G * d->n_kv_heads;
-    const int blocks = (warps + 3) / 4;
+    const int blocks = (warps + 7) / 8;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (d->dtype == LS_F16)
-        attn_combine_kernel<__half><<<blocks, 128, 0, st>>>(*d);
+        attn_combine_kernel<__half><<<blocks, 256, 0, st>>>(*d);
     else
-        attn_combine_kernel<__nv_bfloat16><<<blocks, 128, 0, st>>>(*d);
+        attn_combine_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(*d);
     return check_launch("ls_attn_combine");
 }

@@ -40,6 +40,7 @@ constexpr int KV_STAGE_BYTES = 4 * 8192;           // K c0 | K c1 | V c0 | V c1 
 constexpr int P_BYTES = 128 * 128;                 // one P tile: 128 rows x 64 keys
 constexpr int STATE_BYTES = 3 * NR_MAX * 128 * 4;  // m_ref[384], l[384], version[384]
 constexpr int BAR_BYTES = 256;
+constexpr int SPECIAL_BYTES = 256;                 // special-tile table (12 x 16 B)
 constexpr int SMEM_BYTES = 232448;                 // everything sm_100 allows per CTA (227 KB)
 constexpr int SMEM_USABLE = SMEM_BYTES - 1024;     // minus worst-case 1 KB alignment of the dynamic base
 
@@ -54,6 +55,14 @@ constexpr uint32_t COL_O = 128;                    // 3 x 128
 //   KV  ring of 2..4 stages of 64-key K and V tiles, as many as fit
 //   (P never touches shared memory: the softmax warpgroups store it to TMEM and the PV MMA reads its A operand
 //    from there - shared-memory bandwidth, 128 B/clk, is the scarce resource of this kernel)
+constexpr int MAX_SPECIAL = 12;
+struct SpecialTile {
+    int tok;      // first LOCAL token of the tile (need not be 64-aligned for tail tiles)
+    int n_valid;  // keys of the tile that exist (the rest of the 64-row TMA box is masked)
+    int kind;     // 0 = prefix keys (causal limit applies), 1 = tail keys (tree bit mask applies)
+    int base;     // kind 0: global index of key 0;  kind 1: tail index of key 0
+};
+
 struct Plan {
     int q2_rows, q_bytes, stages, off_kv, off_p, off_state, off_bar;
 };
@@ -62,7 +71,7 @@ __host__ __device__ inline Plan make_plan(int R) {
     const int NR = (R + 127) / 128;
     p.q2_rows = (NR == 3 && R - 256 <= 64) ? 64 : 128;
     p.q_bytes = NR < 3 ? NR * 32768 : 65536 + p.q2_rows * 256;
-    const int fixed = p.q_bytes + STATE_BYTES + BAR_BYTES;
+    const int fixed = p.q_bytes + STATE_BYTES + BAR_BYTES + SPECIAL_BYTES;
     int st = (SMEM_USABLE - fixed) / KV_STAGE_BYTES;
     p.stages = st > MAX_STAGES ? MAX_STAGES : st;
     p.off_kv = p.q_bytes;
@@ -207,7 +216,7 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 template <typename T>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
-               int n_splits_tc) {
+               int n_splits_tc, int fuse) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     const uint32_t sbase = smem_u32(smem);
@@ -221,9 +230,33 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
     const int STAGES = pl.stages;
     const int kv_len = *d.kv_len_ptr + d.kv_len_bias;
     const int total_tiles = tc_full_tiles(d, kv_len, n_q);
-    const int per = (total_tiles + n_splits_tc - 1) / n_splits_tc;
-    const int tile0 = min(split * per, total_tiles);
-    const int n_tiles = min(tile0 + per, total_tiles) - tile0;
+    // With `fuse` the masked remainder rides along as SPECIAL tiles appended to the tile sequence: the prefix keys
+    // behind the last full unmasked tile (partial tile, causal rows) and the tree-masked tail of this round's
+    // tokens.  They come from a small table in shared memory and the softmax applies a per-row bit mask to them.
+    SpecialTile* sp_tiles = reinterpret_cast<SpecialTile*>(smem + pl.off_bar + BAR_BYTES);
+    int n_special = 0;
+    if (fuse) {
+        const int sb = d.kv_shard_begin;
+        const int se = d.kv_shard_end < 0 ? INT_MAX : d.kv_shard_end;
+        const int loc_end = max(min(kv_len, se) - sb, 0);
+        int n = 0;
+        for (int tok = total_tiles * BN; tok < loc_end && n < MAX_SPECIAL; tok += BN, ++n)
+            if (tid == 0) sp_tiles[n] = SpecialTile{tok, min(BN, loc_end - tok), 0, tok + sb};
+        if (d.tail_owner) {
+            const int t0 = kv_len - sb, t1 = t0 + d.n_tail;
+            for (int tok = t0; tok < t1 && n < MAX_SPECIAL; ++n) {
+                const int len = min(min(BN, LS_PAGE - (tok & (LS_PAGE - 1))), t1 - tok);   // never cross a page
+                if (tid == 0) sp_tiles[n] = SpecialTile{tok, len, 1, tok - t0};
+                tok += len;
+            }
+        }
+        n_special = n;
+    }
+    const int all_tiles = total_tiles + n_special;
+    const int per = (all_tiles + n_splits_tc - 1) / n_splits_tc;
+    const int tile0 = min(split * per, all_tiles);
+    const int n_tiles = min(tile0 + per, all_tiles) - tile0;
+    const int first_special = total_tiles - tile0;           // local tile index j >= first_special is special
     const int n_steps = n_tiles * NR;
 
     float* st_m = reinterpret_cast<float*>(smem + pl.off_state);
@@ -280,9 +313,9 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         for (int j = 0; j < n_tiles; ++j) {
             mbar_wait(bar(B_KV_EMPTY + s), ph ^ 1);
             if (elect_one()) {
-                const int tile = tile0 + j;
-                const int page = __ldg(d.page_table + (tile >> 1));
-                const int row = (page * d.n_kv_heads + kvh) * LS_PAGE + (tile & 1) * BN;
+                const int tok = j >= first_special ? sp_tiles[j - first_special].tok : (tile0 + j) * BN;
+                const int page = __ldg(d.page_table + (tok >> 7));
+                const int row = (page * d.n_kv_heads + kvh) * LS_PAGE + (tok & (LS_PAGE - 1));
                 const uint32_t dst = sbase + pl.off_kv + s * KV_STAGE_BYTES;
                 mbar_expect_tx(bar(B_KV_FULL + s), KV_STAGE_BYTES);
                 tma_load_2d(dst, &map_k, 0, row, bar(B_KV_FULL + s));
@@ -388,6 +421,29 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
             tmem_wait_ld();
             tc_fence_before();
             mbar_arrive(bar(B_S_FREE + b));
+            if (j >= first_special) {
+                // per-row visibility word of this tile's 64 key slots
+                const SpecialTile st = sp_tiles[j - first_special];
+                const int rp = r * 128 + row;
+                uint64_t vis = 0ull;
+                if (rp < R) {
+                    const int qi = rp / G;
+                    if (st.kind == 0) {
+                        const int hi = d.causal ? kv_len - (n_q - 1 - qi) : kv_len;      // visible global keys: j < hi
+                        const int cnt = min(max(hi - st.base, 0), st.n_valid);
+                        vis = cnt >= 64 ? ~0ull : ((1ull << cnt) - 1ull);
+                    } else {
+                        const uint64_t* w = d.tail_mask + static_cast<size_t>(qi) * LS_MASK_WORDS;
+                        const int wi = st.base >> 6, sh = st.base & 63;
+                        vis = w[wi] >> sh;
+                        if (sh && wi + 1 < LS_MASK_WORDS) vis |= w[wi + 1] << (64 - sh);
+                        if (st.n_valid < 64) vis &= (1ull << st.n_valid) - 1ull;
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 64; ++e)
+                    if (!((vis >> e) & 1ull)) sv[e] = 0xff800000u;                       // -inf
+            }
             float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
             for (int e = 0; e < 64; e += 8) {
@@ -433,7 +489,8 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                 }
             }
             // p = 2^(s * c2 - m_ref), packed fp32x2 FMA / ADD, four independent partial sums
-            const uint64_t negm = pack2(-m_ref, -m_ref);
+            const float m_use = m_ref == -INFINITY ? 0.f : m_ref;      // row with no visible key so far: p = 2^(-inf) = 0
+            const uint64_t negm = pack2(-m_use, -m_use);
             uint64_t sum_a = 0ull, sum_b = 0ull;                     // {0.f, 0.f}
             uint32_t pk[32];
 #pragma unroll
@@ -560,8 +617,9 @@ static int get_map(const void* pool, long long rows, int dtype, CUtensorMap* out
 }  // namespace ls
 
 // Launch the tensor-core kernel over the unmasked full tiles with `n_splits_tc` splits writing partial slots
-// [part_offset, part_offset + n_splits_tc).  Eligibility is checked by the dispatcher in api.cu.
-extern "C" int ls_attn_partial_tc(const ls_attn_desc* d, int n_splits_tc, void* stream) {
+// [part_offset, part_offset + n_splits_tc).  With `fuse_remainder` the masked remainder (partial tile, causal
+// rows, tree-masked tail) is appended to the tile sequence as special tiles and shared out with the rest.
+static int launch_tc(const ls_attn_desc* d, int n_splits_tc, int fuse_remainder, void* stream) {
     using namespace ls;
     using namespace ls::tc;
     LS_REQUIRE(d && n_splits_tc >= 1, "ls_attn_partial_tc: bad arguments");
@@ -584,8 +642,15 @@ extern "C" int ls_attn_partial_tc(const ls_attn_desc* d, int n_splits_tc, void* 
     dim3 grid(n_splits_tc, d->n_kv_heads);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (d->dtype == LS_F16)
-        attn_tc_kernel<__half><<<grid, THREADS, SMEM_BYTES, st>>>(*d, mk, mv, n_splits_tc);
+        attn_tc_kernel<__half><<<grid, THREADS, SMEM_BYTES, st>>>(*d, mk, mv, n_splits_tc, fuse_remainder);
     else
-        attn_tc_kernel<__nv_bfloat16><<<grid, THREADS, SMEM_BYTES, st>>>(*d, mk, mv, n_splits_tc);
+        attn_tc_kernel<__nv_bfloat16><<<grid, THREADS, SMEM_BYTES, st>>>(*d, mk, mv, n_splits_tc, fuse_remainder);
     return check_launch("ls_attn_partial_tc");
+}
+
+extern "C" int ls_attn_partial_tc(const ls_attn_desc* d, int n_splits_tc, void* stream) { return launch_tc(d, n_splits_tc, 0, stream); }
+// the whole call in one launch: d->n_splits CTAs per kv head share the unmasked and the special tiles
+extern "C" int ls_attn_partial_tc_fused(const ls_attn_desc* d, void* stream) {
+    LS_REQUIRE(d && d->n_splits >= 1, "ls_attn_partial_tc_fused: needs n_splits >= 1");
+    return launch_tc(d, d->n_splits, 1, stream);
 }

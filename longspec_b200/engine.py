@@ -247,8 +247,8 @@ class Engine:
 
         def splits(rows):
             if rows * G <= 384:
-                # tcgen05 path: one CTA per SM over (split, kv head) + one mma.sync split for the masked remainder
-                return int(max(2, self.sms // d.kv_heads + 1))
+                # tcgen05 path: one CTA per SM over (split, kv head); the masked remainder rides along as special tiles
+                return int(max(1, self.sms // d.kv_heads))
             rb = (rows * G + 127) // 128
             return int(max(1, min(tiles, math.ceil(2 * self.sms / (d.kv_heads * rb)), 64)))
         self.n_split_verify = splits(self.q_v)

@@ -28,7 +28,7 @@ q = torch.randn(qv, H, 128, generator=g, device=dev, dtype=torch.float32).to(dt)
 out = torch.empty_like(q)
 G = H // Hk
 sms = _lib.load().ls_sm_count()
-n_splits = int(os.environ.get("SPLITS", sms // Hk + 1))
+n_splits = int(os.environ.get("SPLITS", sms // Hk))
 part_o = torch.empty(n_splits * Hk * qv * G * 128, dtype=torch.float32, device=dev)
 part_l = torch.empty(n_splits * Hk * qv * G, dtype=torch.float32, device=dev)
 kvl = torch.tensor([N], dtype=torch.int32, device=dev)
@@ -61,6 +61,15 @@ for it in range(iters):
 ev1.record()
 torch.cuda.synchronize()
 ms = ev0.elapsed_time(ev1) / iters
+# partial kernel alone / combine alone
+for name in (entry, "ls_attn_combine"):
+    torch.cuda.synchronize()
+    ev0.record()
+    for it in range(iters):
+        _lib.call(name, C.byref(descs[it % layers]), _stream())
+    ev1.record()
+    torch.cuda.synchronize()
+    print(f"   {name} alone: {ev0.elapsed_time(ev1) / iters * 1e3:.1f} us")
 byt = N * 2 * Hk * 128 * 2
 print(f"N={N} splits={n_splits} {entry}+combine: {ms * 1e3:.1f} us/iter, {byt / ms / 1e6:.0f} GB/s, "
       f"{4.0 * (qv - 2) * N * 128 * H / ms / 1e9:.0f} TFLOP/s")
