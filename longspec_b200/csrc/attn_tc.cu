@@ -339,7 +339,6 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         int tp = 0, rp = 0, sp = 0, jp0 = 1;          // next PV step: row tile, kv stage, first-tile flag
         bool kv_ready = false;
         while (tp < n_steps) {
-            bool progressed = false;
             if (tq < n_steps) {
                 const int b = tq & 1;
                 if (rq == 0 && !kv_ready) kv_ready = mbar_test(bar(B_KV_FULL + sq), phq);
@@ -363,7 +362,6 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                         kv_ready = false;
                         if (++sq == STAGES) { sq = 0; phq ^= 1; }
                     }
-                    progressed = true;
                 }
             }
             if (tp < tq && mbar_test(bar(B_P_FULL + (tp & 1)), (tp >> 1) & 1)) {
@@ -385,9 +383,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                     jp0 = 0;
                     if (++sp == STAGES) sp = 0;
                 }
-                progressed = true;
             }
-            if (!progressed) __nanosleep(20);
         }
         if (n_steps > 0 && elect_one()) tc_commit(bar(B_ALL_DONE));   // every MMA of this CTA has completed once this fires
         __syncwarp();
