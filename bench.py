@@ -319,7 +319,9 @@ def main():
 
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)                      # skip NCCL / CUDA-graph teardown (can hang with captured collectives)
         return
     # ---------------- (D) CPU baseline beside it (rank 0, N = 1 only) ----------------
     cpu = None
@@ -352,7 +354,10 @@ def main():
     }
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -1,25 +1,27 @@
-// tcgen05 / TMA / TMEM split-KV attention over the long, unmasked part of the paged prefix.
+// tcgen05 / TMA / TMEM split-KV attention over the paged prefix + the tree-masked tail (ls_attn_partial).
 //
 // One CTA = (split, kv head) and ALL packed query rows of that kv head (up to 3 tiles of 128 rows,
 // r = token * G + head-in-group), so every K/V byte is pulled from HBM once per kv head and reused by the
 // whole GQA group and the whole candidate tree from shared memory.
 //
-//   warp 0  (1 thread)  TMA producer: 64-key K and V tiles (2 x [64 x 128B] boxes each, SWIZZLE_128B) from
-//                       the paged pool into a 3-stage shared-memory ring, completion on mbarriers
-//   warp 1  (1 thread)  MMA issuer: S = Q K^T (M128 N64 K16 x8, A = Q tile in smem, B = K tile, both
-//                       K-major) into a double-buffered TMEM accumulator; O_r += P V (M128 N128 K16 x4,
-//                       A = P tile in smem, B = V tile MN-major) into per-row-tile TMEM accumulators
-//   warp 2              TMEM allocation (512 columns: 2 x 64 for S, 3 x 128 for O)
-//   warps 4-7 / 8-11    two softmax warpgroups, alternating steps: tcgen05.ld the S tile (one row per
-//                       thread), online softmax in the log2 domain with lazy rescaling (O in TMEM is only
-//                       rescaled when a row maximum grows by more than 2^8), P rounded to dtype and written
-//                       to swizzled shared memory for the PV MMA
-// The epilogue writes normalised partial O (fp32) and the natural-log LSE per (split, kv head, row); the
-// shared combine kernel (attn_mma.cu) merges them with the partials of the masked remainder (last partial
-// tile, causal rows, tree-masked tail), which stays on the general mma.sync path.
+//   warp 0              TMA producer: 64-key K and V tiles (2 x [64 x 128B] boxes each, SWIZZLE_128B) from the
+//                       paged pool into a 2-4 stage shared-memory ring, completion on mbarriers
+//   warp 1              MMA issuer (converged warp, one elected lane): S = Q K^T (M128 N64 K16 x8, SS: Q tile and
+//                       K tile K-major in smem) into the TMEM score tile; O_r += P V (M128 N128 K16 x4, TS: P read
+//                       from TMEM, V MN-major in smem) into per-row-tile TMEM accumulators.  Event-driven: a QK
+//                       burst goes out as soon as S is free, a PV burst as soon as P is published.
+//   warp 2              TMEM allocation (512 columns: S 64, P 2 x 32, O 3 x 128)
+//   warps 4-7 / 8-11    two softmax warpgroups, alternating steps: tcgen05.ld the S tile (one row per thread),
+//                       online softmax in the log2 domain with lazy rescaling (O in TMEM is only rescaled when a
+//                       row maximum grows by more than 2^8), P rounded to dtype and tcgen05.st back to TMEM
+// The masked remainder of the call (last partial prefix tile, causal rows, the tree-masked tail = this round's
+// tokens) is appended to the tile sequence as "special tiles" whose softmax applies a per-row bit mask, so one
+// launch covers the whole attention call.  The epilogue writes normalised partial O (fp32) and the natural-log
+// LSE per (split, kv head, row); ls_attn_combine (attn_mma.cu) merges the splits (and, sequence-sharded, the ranks).
 //
 // Reference semantics: flash_attn_with_kvcache(q, K_Cache, V_Cache, cache_seqlens=cache_lens,
-// return_softmax_lse=True) of llama.py:385 and llama_glide.py:297, restated in oracle/flash_ref.py.
+// return_softmax_lse=True) + tree_part_fwd + merge of llama.py:385-421, and llama_glide.py:265,297;
+// restated in oracle/flash_ref.py and oracle/attention.py.
 #include <cuda.h>
 #include <limits.h>
 

@@ -130,8 +130,11 @@ __global__ void __launch_bounds__(kGrowThreads) grow_phase_a(const void* logits,
     }
 }
 
-// Phase B (one CTA, one warp per row then a block-wide merge) + tree state update.
+// Phase B (one CTA) + tree state update.  Phase A left, per (row, chunk), the chunk's top-k in descending order,
+// so the row-level and then the global top-k are k-way merges: one warp per row with the chunk lists spread over
+// its lanes, then one warp over the rows.  Every step is a warp arg-max over list heads - no scans.
 constexpr int kMaxRowsB = 32;
+constexpr int kMaxChunksPerLane = 8;      // vocab <= 32 * 8 * 2048 = 524288
 __global__ void __launch_bounds__(1024) grow_phase_b(ls_tree_state s, int vocab, int n_chunks, int k, int level,
                                                      int level_begin, int n_rows, int n_new, const float* ws_max,
                                                      const float* ws_sum, float* ws_val, const int32_t* ws_idx) {
@@ -140,12 +143,9 @@ __global__ void __launch_bounds__(1024) grow_phase_b(ls_tree_state s, int vocab,
     __shared__ int row_idx[kMaxRowsB][LS_MAX_TOPK];
     __shared__ float fin_val[LS_MAX_TOPK];
     __shared__ long long fin_flat[LS_MAX_TOPK];
-    __shared__ float red_v[32];
-    __shared__ long long red_i[32];
-    __shared__ int red_slot[32];
-    // per row: log-normaliser and row-level top-k of (x - max) - log(sum) + parent score
     if (warp < n_rows) {
         const int row = warp;
+        // log-normaliser of the row from the per-chunk (max, sum exp)
         float mx = -INFINITY;
         for (int c = lane; c < n_chunks; c += 32) mx = fmaxf(mx, ws_max[row * n_chunks + c]);
         mx = warp_max(mx);
@@ -154,72 +154,70 @@ __global__ void __launch_bounds__(1024) grow_phase_b(ls_tree_state s, int vocab,
         sm = warp_sum(sm);
         const float logsum = logf(sm);
         const float hist = level == 0 ? 0.f : s.scores[level_begin + row];
-        const int n_cand = n_chunks * k;
-        float* cv = ws_val + static_cast<size_t>(row) * n_cand;
-        const int32_t* ci = ws_idx + static_cast<size_t>(row) * n_cand;
-        for (int c = lane; c < n_cand; c += 32) {
-            const float x = cv[c];
-            // log_softmax = (x - max) - log(sum)  (torch), then + history (llama_glide.py:1047)
-            cv[c] = x == -INFINITY ? -INFINITY : ((x - mx) - logsum) + hist;
-        }
-        __syncwarp();
+        const float* cv = ws_val + static_cast<size_t>(row) * n_chunks * k;
+        const int32_t* ci = ws_idx + static_cast<size_t>(row) * n_chunks * k;
+        int ptr[kMaxChunksPerLane];
+#pragma unroll
+        for (int q = 0; q < kMaxChunksPerLane; ++q) ptr[q] = 0;
         for (int it = 0; it < n_new; ++it) {
             float bv = -INFINITY;
-            int bi = INT_MAX, bc = -1;
-            for (int c = lane; c < n_cand; c += 32) {
-                const float x = cv[c];
-                const int id = ci[c];
-                if (x > bv || (x == bv && id < bi)) { bv = x; bi = id; bc = c; }
+            int bi = INT_MAX, bq = -1;
+#pragma unroll
+            for (int q = 0; q < kMaxChunksPerLane; ++q) {
+                const int c = lane + q * 32;
+                if (c < n_chunks && ptr[q] < k) {
+                    const float x = cv[c * k + ptr[q]];
+                    const int id = ci[c * k + ptr[q]];
+                    if (x > bv || (x == bv && id < bi)) { bv = x; bi = id; bq = q; }
+                }
             }
+            float wv = bv;
+            int wi = bi, wl = lane;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bc = oc; }
+                const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+                const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+                if (ov > wv || (ov == wv && oi < wi)) { wv = ov; wi = oi; wl = ol; }
+            }
+            if (lane == wl && bq >= 0) {
+#pragma unroll
+                for (int q = 0; q < kMaxChunksPerLane; ++q)
+                    if (q == bq) ++ptr[q];
             }
             if (lane == 0) {
-                row_val[row][it] = bv;
-                row_idx[row][it] = bi;
-                if (bc >= 0) cv[bc] = -INFINITY;
+                // log_softmax = (x - max) - log(sum)  (torch), then + history (llama_glide.py:1047)
+                row_val[row][it] = wv == -INFINITY ? -INFINITY : ((wv - mx) - logsum) + hist;
+                row_idx[row][it] = wi;
             }
-            __syncwarp();
         }
     }
     __syncthreads();
-    // global top-n_new over n_rows * n_new candidates by (score desc, flat index asc)
-    const int total = n_rows * n_new;
-    for (int it = 0; it < n_new; ++it) {
-        float bv = -INFINITY;
-        long long bi = LLONG_MAX;
-        int bslot = -1;
-        for (int c = tid; c < total; c += blockDim.x) {
-            const int r = c / n_new, j = c - r * n_new;
-            const float x = row_val[r][j];
-            const long long flat = static_cast<long long>(r) * vocab + row_idx[r][j];
-            if (x > bv || (x == bv && flat < bi)) { bv = x; bi = flat; bslot = c; }
-        }
+    // global top-n_new over the rows' sorted lists by (score desc, flat index asc): one warp, lane = row
+    if (warp == 0) {
+        int ptr = 0;
+        for (int it = 0; it < n_new; ++it) {
+            float bv = -INFINITY;
+            long long bf = LLONG_MAX;
+            if (lane < n_rows && ptr < n_new) {
+                bv = row_val[lane][ptr];
+                bf = static_cast<long long>(lane) * vocab + row_idx[lane][ptr];
+            }
+            float wv = bv;
+            long long wf = bf;
+            int wl = lane;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            const int os = __shfl_xor_sync(0xffffffffu, bslot, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bslot = os; }
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+                const long long of = __shfl_xor_sync(0xffffffffu, wf, o);
+                const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+                if (ov > wv || (ov == wv && of < wf)) { wv = ov; wf = of; wl = ol; }
+            }
+            if (lane == wl) ++ptr;
+            if (lane == 0) { fin_val[it] = wv; fin_flat[it] = wf; }
         }
-        if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; red_slot[warp] = bslot; }
-        __syncthreads();
-        if (tid == 0) {
-            float fv = red_v[0];
-            long long fi = red_i[0];
-            int fs = red_slot[0];
-            for (int w = 1; w < (blockDim.x >> 5); ++w)
-                if (red_v[w] > fv || (red_v[w] == fv && red_i[w] < fi)) { fv = red_v[w]; fi = red_i[w]; fs = red_slot[w]; }
-            fin_val[it] = fv;
-            fin_flat[it] = fi;
-            if (fs >= 0) row_val[fs / n_new][fs % n_new] = -INFINITY;
-        }
-        __syncthreads();
     }
+    __syncthreads();
     // tree update (llama_glide.py:1022-1027 for level 0, 1066-1075 for level >= 1)
     const int new_begin = level == 0 ? 1 : level_begin + n_rows;
     int dl = *s.draft_len;
@@ -477,6 +475,7 @@ extern "C" int ls_tree_grow(const ls_tree_state* s, const void* logits, int32_t 
     LS_REQUIRE(n_rows >= 1 && n_rows <= kMaxRowsB, "ls_tree_grow: level width %d out of range [1,%d]", n_rows, kMaxRowsB);
     LS_REQUIRE(level >= 0 && level < s->gamma, "ls_tree_grow: level %d out of range", level);
     LS_REQUIRE(vocab >= n_new, "ls_tree_grow: vocab smaller than n_new");
+    LS_REQUIRE((vocab + kChunk - 1) / kChunk <= 32 * kMaxChunksPerLane, "ls_tree_grow: vocab %d too large", vocab);
     const int new_begin = level == 0 ? 1 : level_end;
     LS_REQUIRE(new_begin + n_new <= s->fseq, "ls_tree_grow: level overflows fseq");
     const int n_chunks = (vocab + kChunk - 1) / kChunk;

@@ -295,19 +295,13 @@ class Engine:
         self.launches += 2
 
     def _exchange_partials(self, a, q_rows):
-        """Sequence-sharded prefix: all-gather the per-rank (O, lse) partial slots (one NCCL
-        exchange per attention call; SURVEY.md section 8(e) option A - deterministic merge order)."""
-        import torch.distributed as dist
+        """Sequence-sharded prefix: one NCCL all-gather of the per-rank (O, lse) partial slots per attention
+        call (SURVEY.md section 8(e) option A - deterministic merge order on every rank)."""
+        from .parallel import exchange_partials
         d = self.dims
         G = d.heads // d.kv_heads
-        per_o = a.n_splits * d.kv_heads * q_rows * G * 128
-        per_l = a.n_splits * d.kv_heads * q_rows * G
-        W = self.shard.world
-        o_all = self.part_o[:per_o * W]
-        l_all = self.part_lse[:per_l * W]
-        r = self.shard.rank
-        dist.all_gather_into_tensor(o_all, o_all[r * per_o:(r + 1) * per_o].clone(), group=self.group)
-        dist.all_gather_into_tensor(l_all, l_all[r * per_l:(r + 1) * per_l].clone(), group=self.group)
+        n_l = a.n_splits * d.kv_heads * q_rows * G
+        exchange_partials(self.part_o, self.part_lse, n_l * 128, n_l, self.shard.rank, self.shard.world, self.group)
 
     def _rope_append(self, q, k, v, q_stride, kv_stride, positions, pools, layer, base_len_ptr, base_bias, slot_offset,
                      n_rows_ptr, rows, append=True):

@@ -165,3 +165,16 @@ def draft_self_tree_attention(q, k_new, v_new, K_cache, V_cache, cache_lens, tre
         cur = cur[0].permute(1, 0, 2)                                    # M,H,D
         outs.append(prefix_o[b].float() * w + cur * (1 - w))
     return torch.stack(outs)
+
+
+def merge_partials(part_o, part_lse):
+    """Associative combine of split-KV partials: part_o (P, rows, D) normalised outputs, part_lse (P, rows)
+    natural-log normalisers (-inf for an empty part).  The same operator the reference uses between its
+    prefix and tree parts (weight = sigmoid(lse_a - lse_b), llama.py:387,420), generalised to P parts."""
+    mx = part_lse.max(dim=0).values
+    mx_safe = torch.where(torch.isinf(mx), torch.zeros_like(mx), mx)
+    w = torch.exp(part_lse - mx_safe)
+    w = torch.where(torch.isinf(part_lse), torch.zeros_like(w), w)
+    den = w.sum(0)
+    out = (w.unsqueeze(-1) * part_o).sum(0) / torch.where(den == 0, torch.ones_like(den), den).unsqueeze(-1)
+    return out
