@@ -36,7 +36,9 @@ sys.path.insert(0, ROOT)
 MODEL = os.environ.get("LONGSPEC_BENCH_MODEL", "llama3-8b-262k")
 PROMPT = int(os.environ.get("LONGSPEC_BENCH_PROMPT", 131072))
 TREE = [int(x) for x in os.environ.get("LONGSPEC_BENCH_TREE", "4 16 16 16 16").split()]
-DRAFT_SCALE = os.environ.get("LONGSPEC_BENCH_DRAFT_SCALE")
+# draft noise 2.6 gives tau ~ 3.3 with the synthetic weights (tools/tau_sweep.py), the accepted length the reference
+# publishes for Llama-3-8B (2.99-3.39)
+DRAFT_SCALE = os.environ.get("LONGSPEC_BENCH_DRAFT_SCALE", "2.6")
 METRIC = "decode_tokens_per_s"
 UNIT = "tokens/s"
 

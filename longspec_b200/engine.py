@@ -247,8 +247,9 @@ class Engine:
 
         def splits(rows):
             if rows * G <= 384:
-                # tcgen05 path: one CTA per SM over (split, kv head); the masked remainder rides along as special tiles
-                return int(max(1, self.sms // d.kv_heads))
+                # tcgen05 path: one CTA per SM over (split, kv head); the masked remainder rides along as special
+                # tiles.  Short contexts take fewer splits (>= 8 tiles per CTA) to keep the partial traffic down.
+                return int(max(1, min(self.sms // d.kv_heads, (tiles + 7) // 8)))
             rb = (rows * G + 127) // 128
             return int(max(1, min(tiles, math.ceil(2 * self.sms / (d.kv_heads * rb)), 64)))
         self.n_split_verify = splits(self.q_v)

@@ -130,11 +130,34 @@ class LlamaGlide:
         stop_id = self.eos_token_id
         num = 0
         pos = eng.p_cache_len
+        tok_in = out[0:1].clone()
+        tok_out = torch.zeros(1, dtype=torch.int64, device=self.device)
+        idx = torch.ones(1, dtype=torch.int64, device=self.device)
+
+        def step():
+            # one token: append at cache_len, causal attention, argmax (llama_glide.py:572-577), all on the device
+            eng.decode_one(tok_in, pos, tok_out)
+            eng.p_cache_len.add_(1)
+            out.scatter_(0, idx, tok_out)
+            idx.add_(1)
+            tok_in.copy_(tok_out)
+
+        graph = None
         torch.cuda.synchronize()
         t0 = time.time()
         for i in range(1, max_gen_len):
-            eng.decode_one(out[i - 1:i], pos, out[i:i + 1])
-            eng.p_cache_len += 1
+            if graph is not None:
+                graph.replay()
+            else:
+                step()
+                if self.use_graph and i == 1:
+                    graph = torch.cuda.CUDAGraph()
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        with torch.cuda.graph(graph, stream=side):
+                            step()
+                    torch.cuda.current_stream().wait_stream(side)
             num += 1
             if stop_id is not None and i % 16 == 0 and bool((out[:i + 1] == stop_id).any()):
                 break           # the reference tests every step (578); the tail is trimmed below
