@@ -265,6 +265,7 @@ def main():
     eng, graph = m.eng, m.last_graph
     assert graph is not None, "CUDA graph capture is required for the device-timed number"
     st = eng.st
+    st["counters"][3] = 0                    # a set stop flag would turn the replayed rounds' acceptance into no-ops
     for _ in range(W):
         graph.replay()
     barrier()

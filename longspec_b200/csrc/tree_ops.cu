@@ -343,6 +343,9 @@ __global__ void __launch_bounds__(256) tree_accept_kernel(ls_tree_state s, const
                                                           const int32_t* page_table, int n_kv_heads, int non_leaf_len,
                                                           int64_t stop_id, int kv_bias) {
     const int tid = threadIdx.x;
+    // A round that was queued before the host saw the stop flag must not change the result: once the flag is set,
+    // acceptance is a no-op (output_ids, counters and the accepted state stay final).
+    if (s.counters[3] != 0) return;
     __shared__ int sh_last, sh_acc;
     __shared__ int sh_map[64 * W];
     __shared__ unsigned char sh_ok[64 * W];

@@ -198,31 +198,51 @@ class LlamaGlide:
         st["counters"].copy_(torch.tensor([0, 1, 1, 0], dtype=torch.int32))
         # the reference tests the WHOLE output buffer (pre-fill value and first token included)
         sticky_stop = stop_id >= 0 and (first == stop_id or (fill == stop_id and max_gen_len > 1))
-        host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        # Pipelined host loop: round r+1 is enqueued BEFORE round r's 16-byte result is read, so the GPU never waits
+        # for the host (graph launch, D2H, Python).  A round enqueued after the stop condition is harmless:
+        # ls_tree_accept is a no-op once the device-side stop flag is set.
+        hosts = [torch.zeros(4, dtype=torch.int32).pin_memory() for _ in range(2)]
+        events = [torch.cuda.Event(), torch.cuda.Event()]
         graph = None
         rounds = 0
         round_log = []                       # (host time, tokens written) after every round's stop test
         launches0 = eng.launches
-        torch.cuda.synchronize()
-        start_time = time.time()
-        for _ in range(1, max_gen_len):
+        limit = max_gen_len - 1 if max_rounds is None else min(max_gen_len - 1, max_rounds)
+
+        queued = 0                           # rounds enqueued so far
+
+        def enqueue():
+            nonlocal queued
             if graph is not None:
                 graph.replay()
             else:
                 eng.round(stop_id)
-            host.copy_(st["counters"], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            hosts[queued % 2].copy_(st["counters"], non_blocking=True)
+            events[queued % 2].record()
+            queued += 1
+
+        torch.cuda.synchronize()
+        start_time = time.time()
+        host = hosts[0]
+        if limit >= 1:
+            enqueue()                        # round 0 runs eagerly
+        while rounds < queued:
+            if rounds == 0:
+                events[0].synchronize()
+                self.launches_per_round = eng.launches - launches0
+                if self.use_graph and not sticky_stop:
+                    graph = self._capture_round(eng, stop_id)
+            # keep one more round in flight before blocking on this round's result
+            if queued == rounds + 1 and queued < limit and not sticky_stop:
+                enqueue()
+            events[rounds % 2].synchronize()
+            host = hosts[rounds % 2]
+            stop_now = bool(host[3] != 0) or sticky_stop
             rounds += 1
             round_log.append((time.time(), int(host[2])))
-            if rounds == 1:
-                self.launches_per_round = eng.launches - launches0
-            if host[3] != 0 or sticky_stop:
+            if stop_now or rounds >= limit:
                 break
-            if max_rounds is not None and rounds >= max_rounds:
-                break
-            if self.use_graph and graph is None and rounds == 1:
-                graph = self._capture_round(eng, stop_id)
-        torch.cuda.synchronize()
+        host = host.clone()
         elapsed_time = time.time() - start_time
         count = torch.tensor(int(host[0]), device=self.device)
         num = int(host[1])
