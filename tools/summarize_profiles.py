@@ -1,0 +1,115 @@
+"""Condense gpurun_out/ ncu artefacts into small text files under profiles/ (tracked).
+   python tools/summarize_profiles.py <tag>      e.g. r01a
+Inputs (whatever exists): gpurun_out/launches_bench.csv (ncu --metrics gpu__time_duration.sum of bench.py),
+gpurun_out/attn_tc_full.ncu-rep (ncu --set full of the dominant kernel), bench.json, prof_*.txt."""
+import csv
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+from collections import OrderedDict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+os.makedirs(PROF, exist_ok=True)
+
+
+def short(name):
+    name = re.sub(r"\(.*", "", name)
+    name = re.sub(r"^void ", "", name)
+    return name[:80]
+
+
+def launches():
+    p = os.path.join(OUT, "launches_bench.csv")
+    if not os.path.exists(p):
+        return
+    rows = []
+    with open(p, newline="") as f:
+        lines = [ln for ln in f if ln.startswith('"')]
+    for r in csv.DictReader(lines):
+        if r["Metric Name"] != "gpu__time_duration.sum":
+            continue
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r["Metric Unit"]
+        us = v / 1e3 if unit in ("ns", "nsecond") else v * (1e3 if unit in ("ms", "msecond") else 1.0)
+        rows.append((int(r["ID"]), short(r["Kernel Name"]), r["Grid Size"], r["Block Size"], us))
+    # the decode rounds are the launches after the last ls_round_begin-delimited boundary: take the LAST full round
+    idx = [i for i, r in enumerate(rows) if "round_begin" in r[1]]
+    with open(os.path.join(PROF, f"{tag}_launches_bench.txt"), "w") as f:
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 2 --warmup 3 --no-cpu-baseline\n")
+        f.write(f"# {len(rows)} launches in the process (prefill + eager round + graph rounds + roofline loop); "
+                f"{len(idx)} decode rounds seen.\n# Per-launch times are cold-cache and serialised: compare SHARES.\n")
+        if len(idx) >= 2:
+            a, b = idx[-2], idx[-1]
+            rnd = rows[a:b]
+            tot = sum(r[4] for r in rnd)
+            f.write(f"\n## one decode round (launch {rows[a][0]}..{rows[b][0] - 1}): {len(rnd)} launches, {tot / 1e3:.3f} ms serialised\n")
+            agg = OrderedDict()
+            for r in rnd:
+                k = agg.setdefault(r[1], [0, 0.0])
+                k[0] += 1
+                k[1] += r[4]
+            f.write(f"{'share':>7} {'total us':>10} {'n':>5} {'avg us':>9}  kernel\n")
+            for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
+                f.write(f"{100 * t / tot:6.1f}% {t:10.1f} {n:5d} {t / n:9.1f}  {k}\n")
+            f.write("\n## the same round, launch by launch\n# id, us, grid, block, kernel\n")
+            for r in rnd:
+                f.write(f"{r[0]},{r[4]:.1f},{r[2]},{r[3]},{r[1]}\n")
+    print("launch list:", len(rows), "launches,", len(idx), "rounds")
+
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "sm__cycles_elapsed.avg",
+        "sm__cycles_elapsed.avg.per_second", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "smsp__inst_executed.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "smsp__inst_executed_pipe_xu.sum", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "launch__shared_mem_per_block_dynamic", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active"]
+
+
+def full(rep_name="attn_tc_full"):
+    rep = os.path.join(OUT, rep_name + ".ncu-rep")
+    if not os.path.exists(rep):
+        return
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    with open(os.path.join(PROF, f"{tag}_{rep_name}_summary.txt"), "w") as f:
+        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:attn_tc  python tools/prof_attn.py 131072 3\n"
+                f"# one row per captured launch ({len(data)} launches)\n")
+        for i, h in enumerate(hdr):
+            if h in KEYS or h == "Kernel Name":
+                f.write(f"{h} [{units[i]}]: " + " | ".join(r[i][:70] for r in data) + "\n")
+        src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+        rs = list(csv.reader(src.splitlines()))
+        his = [i for i, r in enumerate(rs) if r and r[0] == "Address"]
+        if his:
+            hi, end = his[0], (his[1] - 1 if len(his) > 1 else len(rs))
+            h = rs[hi]
+            ix = {n: i for i, n in enumerate(h)}
+            d = [r for r in rs[hi + 1:end] if len(r) == len(h)]
+            S = lambda r: int(r[ix["# Samples"]] or 0)
+            stalls = [n for n in h if n.startswith("stall_") and "Not" not in n]
+            tot = sum(S(r) for r in d)
+            agg = sorted(((sum(int(r[ix[n]] or 0) for r in d), n) for n in stalls), reverse=True)
+            f.write(f"\n## warp-state samples, first launch: {tot} samples over {len(d)} SASS instructions\n")
+            f.write(", ".join(f"{n}={v}" for v, n in agg[:8]) + "\n")
+            f.write("\n## top instructions by samples (samples, top stall, SASS)\n")
+            for r in sorted(d, key=lambda r: -S(r))[:30]:
+                st = max(((int(r[ix[n]] or 0), n) for n in stalls))
+                f.write(f"{S(r):6d}  {st[1]:<24} {r[ix['Source']][:100]}\n")
+    print("ncu full summary written")
+
+
+launches()
+full()
+for name in ("bench.json", "prof_attn_128k.txt", "prof_attn_16k.txt", "prof_round_128k.txt", "pytest_gpu.log", "smoke.log", "gpu.txt"):
+    p = os.path.join(OUT, name)
+    if os.path.exists(p):
+        shutil.copy(p, os.path.join(PROF, f"{tag}_{name}"))
