@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) attn_partial_kernel(const ls_a
     const int loc_end = max(min(kv_len, se) - sb, 0);                 // local prefix end
     int loc_beg = 0;
     if (d.window >= 0) loc_beg = min(max(kv_len - n_q - d.window - sb, 0), loc_end);
-    if (remainder) loc_beg = min(tc_full_tiles(d, kv_len, n_q) * kBN, loc_end);   // the rest is on the tcgen05 kernel
+    if (remainder) loc_beg = min(tc_full_tiles(d, kv_len, n_q) * 128, loc_end);   // the rest is on the tcgen05 kernel
     TilePlan tp;
     {
         const int tb = loc_beg / kBN, te = (loc_end + kBN - 1) / kBN;

@@ -1,23 +1,30 @@
 // tcgen05 / TMA / TMEM split-KV attention over the paged prefix + the tree-masked tail (ls_attn_partial).
 //
-// One CTA = (split, kv head) and ALL packed query rows of that kv head (up to 3 tiles of 128 rows,
-// r = token * G + head-in-group), so every K/V byte is pulled from HBM once per kv head and reused by the
-// whole GQA group and the whole candidate tree from shared memory.
+// Work unit: one CTA = (kv head, a share of the 128-key tiles, up to TWO row tiles of 128 packed query rows),
+// a packed row being r = token * G + head-in-group, so a K/V tile serves the whole GQA group and candidate tree.
 //
-//   warp 0              TMA producer: 64-key K and V tiles (2 x [64 x 128B] boxes each, SWIZZLE_128B) from the
-//                       paged pool into a 2-4 stage shared-memory ring, completion on mbarriers
-//   warp 1              MMA issuer (converged warp, one elected lane): S = Q K^T (M128 N64 K16 x8, SS: Q tile and
-//                       K tile K-major in smem) into the TMEM score tile; O_r += P V (M128 N128 K16 x4, TS: P read
-//                       from TMEM, V MN-major in smem) into per-row-tile TMEM accumulators.  Event-driven: a QK
-//                       burst goes out as soon as S is free, a PV burst as soon as P is published.
-//   warp 2              TMEM allocation (512 columns: S 64, P 2 x 32, O 3 x 128)
-//   warps 4-7 / 8-11    two softmax warpgroups, alternating steps: tcgen05.ld the S tile (one row per thread),
-//                       online softmax in the log2 domain with lazy rescaling (O in TMEM is only rescaled when a
-//                       row maximum grows by more than 2^8), P rounded to dtype and tcgen05.st back to TMEM
+// TMEM (512 columns) holds two 128-column S/P buffers and two 128-column O accumulators - the FA4 shape: two
+// independent QK -> softmax -> PV chains are in flight and every MMA is N = 128 (tensor-rate, not shared-memory
+// bound).  A call with three row tiles (the Llama-3 verify shape: 74 tokens x GQA-4 = 296 rows) is cut into
+// "trios": two HEAVY CTAs (row tiles 0-1, alternate key tiles of the group's range) and one LIGHT CTA (row tile 2,
+// every key tile of the range).  All three do the same number of (row tile, key tile) steps, and the light CTA's
+// K/V loads hit L2 behind the heavy CTAs' loads, so HBM still sees every byte once.
+//
+//   warp 0              TMA producer: 128-key K and V tiles (2 x [128 x 128 B] boxes each, SWIZZLE_128B) from the
+//                       paged pool into separate 2-stage K and V rings, completion on mbarriers
+//   warp 1              MMA issuer (converged warp, one elected lane): S = Q K^T (M128 N128 K16 x8, SS) into S/P
+//                       buffer t & 1; O_r += P V (M128 N128 K16 x8, TS: P read from TMEM, V MN-major in smem).
+//                       In-order schedule  QK(0) QK(1) | P(0): PV(0) QK(2) | P(1): PV(1) QK(3) | ...  - MMAs of one
+//                       thread execute in issue order, so QK(t+2) cannot overwrite the buffer PV(t) still reads.
+//   warp 2              TMEM allocation
+//   warps 4-7 / 8-11    two softmax warpgroups, alternating steps (with two row tiles: one warpgroup per row tile).
+//                       One row per thread, the 128-key tile in two 64-key halves: tcgen05.ld, online softmax in the
+//                       log2 domain with lazy rescaling (O in TMEM is only rescaled when a row maximum grows by more
+//                       than 2^8), P rounded to dtype and tcgen05.st IN PLACE over the S columns it came from.
 // The masked remainder of the call (last partial prefix tile, causal rows, the tree-masked tail = this round's
 // tokens) is appended to the tile sequence as "special tiles" whose softmax applies a per-row bit mask, so one
 // launch covers the whole attention call.  The epilogue writes normalised partial O (fp32) and the natural-log
-// LSE per (split, kv head, row); ls_attn_combine (attn_mma.cu) merges the splits (and, sequence-sharded, the ranks).
+// LSE per (slot, kv head, row); ls_attn_combine (attn_mma.cu) merges the slots (and, sequence-sharded, the ranks).
 //
 // Reference semantics: flash_attn_with_kvcache(q, K_Cache, V_Cache, cache_seqlens=cache_lens,
 // return_softmax_lse=True) + tree_part_fwd + merge of llama.py:385-421, and llama_glide.py:265,297;
@@ -34,58 +41,40 @@
 namespace ls {
 namespace tc {
 
-constexpr int BN = 64;
-constexpr int NR_MAX = 3;
-constexpr int MAX_STAGES = 4;
+constexpr int BN = 128;                            // keys per tile
+constexpr int NRL_MAX = 2;                         // row tiles per CTA
+constexpr int NR_MAX = 3;                          // row tiles per call
+constexpr int STAGES = 2;                          // K ring and V ring depth
 constexpr int THREADS = 384;
-constexpr int KV_STAGE_BYTES = 4 * 8192;           // K c0 | K c1 | V c0 | V c1   (64 keys)
-constexpr int P_BYTES = 128 * 128;                 // one P tile: 128 rows x 64 keys
-constexpr int STATE_BYTES = 3 * NR_MAX * 128 * 4;  // m_ref[384], l[384], version[384]
+constexpr int TILE_BYTES = 32768;                  // one K or V tile: [2 x 64-element chunks][128 keys][128 B]
+constexpr int Q_BYTES = NRL_MAX * 32768;           // [row tile][2 k-chunks][128 rows][128 B]
+constexpr int STATE_BYTES = 2 * 2 * 128 * 4;       // epilogue exchange of (m_ref, l) between the warpgroups
 constexpr int BAR_BYTES = 256;
 constexpr int SPECIAL_BYTES = 256;                 // special-tile table (12 x 16 B)
-constexpr int SMEM_BYTES = 232448;                 // everything sm_100 allows per CTA (227 KB)
-constexpr int SMEM_USABLE = SMEM_BYTES - 1024;     // minus worst-case 1 KB alignment of the dynamic base
+constexpr int OFF_K = Q_BYTES;
+constexpr int OFF_V = OFF_K + STAGES * TILE_BYTES;
+constexpr int OFF_STATE = OFF_V + STAGES * TILE_BYTES;
+constexpr int OFF_BAR = OFF_STATE + STATE_BYTES;
+constexpr int OFF_SPECIAL = OFF_BAR + BAR_BYTES;
+constexpr int SMEM_BYTES = OFF_SPECIAL + SPECIAL_BYTES + 1024;   // + worst-case alignment of the dynamic base
 
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t COL_S = 0;                      // one 128 x 64 fp32 score tile
-constexpr uint32_t COL_P = 64;                     // two 128 x 64 bf16/fp16 probability tiles (32 columns each)
-constexpr uint32_t COL_O = 128;                    // 3 x 128
+constexpr int NBUF = 4;                            // S/P buffers = QK -> softmax -> PV chains in flight
+constexpr uint32_t COL_SP = 0;                     // four buffers of 64 columns: a 128 x 64 fp32 score tile, overwritten
+                                                   // in place by its 128 x 64 bf16/fp16 probability tile (32 columns)
+constexpr uint32_t COL_O = 256;                    // 2 x 128
 
-// Shared-memory plan (all regions 1 KB aligned for SWIZZLE_128B):
-//   Q   row tiles 0,1: [2 k-chunks][128 rows][128 B]; row tile 2 keeps only 64 rows when it has <= 64 valid rows
-//       (the M=128 MMA then reads 64 rows of whatever follows - those S rows belong to padding and are never used)
-//   KV  ring of 2..4 stages of 64-key K and V tiles, as many as fit
-//   (P never touches shared memory: the softmax warpgroups store it to TMEM and the PV MMA reads its A operand
-//    from there - shared-memory bandwidth, 128 B/clk, is the scarce resource of this kernel)
 constexpr int MAX_SPECIAL = 12;
 struct SpecialTile {
-    int tok;      // first LOCAL token of the tile (need not be 64-aligned for tail tiles)
-    int n_valid;  // keys of the tile that exist (the rest of the 64-row TMA box is masked)
+    int tok;      // first LOCAL token of the tile (need not be 128-aligned for tail tiles)
+    int n_valid;  // keys of the tile that exist (the rest of the 128-row TMA box is masked)
     int kind;     // 0 = prefix keys (causal limit applies), 1 = tail keys (tree bit mask applies)
     int base;     // kind 0: global index of key 0;  kind 1: tail index of key 0
 };
 
-struct Plan {
-    int q2_rows, q_bytes, stages, off_kv, off_p, off_state, off_bar;
-};
-__host__ __device__ inline Plan make_plan(int R) {
-    Plan p;
-    const int NR = (R + 127) / 128;
-    p.q2_rows = (NR == 3 && R - 256 <= 64) ? 64 : 128;
-    p.q_bytes = NR < 3 ? NR * 32768 : 65536 + p.q2_rows * 256;
-    const int fixed = p.q_bytes + STATE_BYTES + BAR_BYTES + SPECIAL_BYTES;
-    int st = (SMEM_USABLE - fixed) / KV_STAGE_BYTES;
-    p.stages = st > MAX_STAGES ? MAX_STAGES : st;
-    p.off_kv = p.q_bytes;
-    p.off_p = 0;
-    p.off_state = p.off_kv + p.stages * KV_STAGE_BYTES;
-    p.off_bar = p.off_state + STATE_BYTES;
-    return p;
-}
-
-// P_FULL / P_FREE are indexed by step parity (= softmax warpgroup = P buffer).  Every barrier is waited on
-// phase by phase by its waiter, so mbarrier parity waits can never alias.
-enum { B_KV_FULL = 0, B_KV_EMPTY = 4, B_S_FULL = 8, B_S_FREE = 10, B_P_FULL = 12, B_P_FREE = 14, B_PV_DONE = 16, B_ALL_DONE = 19, B_COUNT = 20 };
+// S_FULL / P_FULL are indexed by pair parity (pair p = steps 2p, 2p+1).  Every barrier is waited on phase by phase
+// by its waiter (or provably at most one phase behind), so mbarrier parity waits can never alias.
+enum { B_K_FULL = 0, B_K_EMPTY = 2, B_V_FULL = 4, B_V_EMPTY = 6, B_S_FULL = 8, B_P_FULL = 10, B_ALL_DONE = 12, B_COUNT = 13 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -136,7 +125,7 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 // one 32-bit add.  Issued by one elected lane of a fully converged warp (operands stay in uniform registers).
 constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
 constexpr uint32_t LBO_K = (16u >> 4) << 16;         // K-major operands (Q, K, P)
-constexpr uint32_t LBO_V = (8192u >> 4) << 16;       // MN-major V: 64-column chunks are 8 KB apart
+constexpr uint32_t LBO_V = (16384u >> 4) << 16;      // MN-major V: 64-column chunks are 16 KB apart
 __device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t"
@@ -215,27 +204,41 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Optional event trace of CTA (0, 0) for tools/trace_attn.py (compiled in only with -DLS_TC_TRACE)
+#ifdef LS_TC_TRACE
+__device__ int g_dbg = 0;     // timing experiments (results become wrong): 1 no PV MMAs, 2 no QK MMAs, 4 no softmax math
+#define LS_DBG(bit) (dbg & (bit))
+__device__ long long* g_trace = nullptr;
+#define LS_TRACE_INIT long long* const trace_buf = (blockIdx.x == 0 && blockIdx.y == 0) ? g_trace : nullptr; const int dbg = g_dbg;
+#define LS_TRACE(ev, t)                                                       \
+    do {                                                                      \
+        if (trace_buf && (t) < 512) trace_buf[(ev) * 512 + (t)] = clock64();  \
+    } while (0)
+#else
+#define LS_TRACE_INIT
+#define LS_TRACE(ev, t) do { } while (0)
+#define LS_DBG(bit) 0
+#endif
+
 template <typename T>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
-               int n_splits_tc, int fuse) {
+               int n_slots, int fuse) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int split = blockIdx.x, kvh = blockIdx.y;
+    const int bx = blockIdx.x, kvh = blockIdx.y;
+    LS_TRACE_INIT
     const int G = d.n_heads / d.n_kv_heads;
     const int n_q = min(*d.n_q_ptr, d.q_rows);
     const int R = n_q * G;
-    const int NR = (R + 127) / 128;                         // row tiles in use (1..3)
-    const Plan pl = make_plan(R);
-    const int STAGES = pl.stages;
     const int kv_len = *d.kv_len_ptr + d.kv_len_bias;
     const int total_tiles = tc_full_tiles(d, kv_len, n_q);
     // With `fuse` the masked remainder rides along as SPECIAL tiles appended to the tile sequence: the prefix keys
     // behind the last full unmasked tile (partial tile, causal rows) and the tree-masked tail of this round's
     // tokens.  They come from a small table in shared memory and the softmax applies a per-row bit mask to them.
-    SpecialTile* sp_tiles = reinterpret_cast<SpecialTile*>(smem + pl.off_bar + BAR_BYTES);
+    SpecialTile* sp_tiles = reinterpret_cast<SpecialTile*>(smem + OFF_SPECIAL);
     int n_special = 0;
     if (fuse) {
         const int sb = d.kv_shard_begin;
@@ -247,7 +250,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         if (d.tail_owner) {
             const int t0 = kv_len - sb, t1 = t0 + d.n_tail;
             for (int tok = t0; tok < t1 && n < MAX_SPECIAL; ++n) {
-                const int len = min(min(BN, LS_PAGE - (tok & (LS_PAGE - 1))), t1 - tok);   // never cross a page
+                const int len = min(LS_PAGE - (tok & (LS_PAGE - 1)), t1 - tok);   // never cross a page
                 if (tid == 0) sp_tiles[n] = SpecialTile{tok, len, 1, tok - t0};
                 tok += len;
             }
@@ -255,25 +258,46 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         n_special = n;
     }
     const int all_tiles = total_tiles + n_special;
-    const int per = (all_tiles + n_splits_tc - 1) / n_splits_tc;
-    const int tile0 = min(split * per, all_tiles);
-    const int n_tiles = min(tile0 + per, all_tiles) - tile0;
-    const int first_special = total_tiles - tile0;           // local tile index j >= first_special is special
-    const int n_steps = n_tiles * NR;
 
-    float* st_m = reinterpret_cast<float*>(smem + pl.off_state);
-    float* st_l = st_m + NR_MAX * 128;
-    uint32_t* st_ver = reinterpret_cast<uint32_t*>(st_l + NR_MAX * 128);   // key tiles already folded into (m, l) of a row
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + pl.off_bar + B_COUNT * 8);
-    const uint32_t bar0 = sbase + pl.off_bar;
+    // ---- role of this CTA (see the header comment) -------------------------------------------------
+    // NRS row tiles are planned from the STATIC q_rows; the rows that exist at run time (R) only gate the math.
+    const int NRS = (d.q_rows * G + 127) / 128;
+    int slot = bx, rt0 = 0, share0 = bx, nshare = 1, first = 0, empty_slot = -1;
+    if (NRS > NRL_MAX) {
+        const bool light = bx >= n_slots;
+        const int g = light ? bx - n_slots : bx >> 1;
+        share0 = 2 * g;
+        nshare = min(2, n_slots - share0);
+        if (light) { slot = share0; rt0 = NRL_MAX; empty_slot = nshare == 2 ? share0 + 1 : -1; }
+        else { first = bx & 1; }
+    }
+    const int stride = (NRS > NRL_MAX && rt0 == 0) ? nshare : 1;
+    const int NR = max(min((R + 127) / 128 - rt0, NRL_MAX), 0);      // local row tiles with at least one live row
+    const int per = (all_tiles + n_slots - 1) / n_slots;
+    const int tile_lo = min(share0 * per, all_tiles) + first;
+    const int tile_hi = min((share0 + nshare) * per, all_tiles);
+    const int n_tiles = (NR > 0 && tile_hi > tile_lo) ? (tile_hi - tile_lo + stride - 1) / stride : 0;
+    // A step = (key tile j, 64-key half h, row tile r), in that nesting; step t runs on S/P buffer t & 3 and its PV
+    // accumulates into O accumulator t & 1, which softmax warpgroup t & 1 owns.  With two row tiles that is "one
+    // warpgroup and one accumulator per row tile"; with one row tile the two warpgroups take alternate key halves
+    // into two accumulators with private (m, l) row states, merged in the epilogue.
+    const int spt = 2 * NR;                                          // steps per key tile
+    const int n_steps = n_tiles * spt;
+    auto tile_index = [&](int j) { return tile_lo + j * stride; };   // position in the call's tile sequence
+
+    float* st_m = reinterpret_cast<float*>(smem + OFF_STATE);        // epilogue exchange only (one row tile)
+    float* st_l = st_m + 2 * 128;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + B_COUNT * 8);
+    const uint32_t bar0 = sbase + OFF_BAR;
     auto bar = [&](int i) { return bar0 + i * 8; };
 
     // ---- one-time setup ----------------------------------------------------------------------------
     if (tid == 0) {
-        for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(bar(B_KV_FULL + i), 1); mbar_init(bar(B_KV_EMPTY + i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar(B_S_FULL + i), 1); mbar_init(bar(B_S_FREE + i), 128); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar(B_P_FULL + i), 128); mbar_init(bar(B_P_FREE + i), 1); }
-        for (int i = 0; i < NR_MAX; ++i) mbar_init(bar(B_PV_DONE + i), 1);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(bar(B_K_FULL + i), 1); mbar_init(bar(B_K_EMPTY + i), 1);
+            mbar_init(bar(B_V_FULL + i), 1); mbar_init(bar(B_V_EMPTY + i), 1);
+        }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar(B_S_FULL + i), 1); mbar_init(bar(B_P_FULL + i), 256); }
         mbar_init(bar(B_ALL_DONE), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -281,21 +305,19 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int i = tid; i < NR_MAX * 128; i += THREADS) { st_m[i] = -INFINITY; st_l[i] = 0.f; st_ver[i] = 0u; }
     // Q tiles -> swizzled shared memory (K-major, SWIZZLE_128B): [tile][k-chunk][row][128B]
-    {
+    if (n_steps > 0) {
         const T* __restrict__ q = reinterpret_cast<const T*>(d.q);
-        const int rows_total = NR < 3 ? NR * 128 : 256 + pl.q2_rows;
-        for (int idx = tid; idx < rows_total * 16; idx += THREADS) {
-            const int rp = idx >> 4, chunk = idx & 15;
-            const int tile = rp >> 7, row = rp & 127;
-            const int chunk_stride = tile < 2 ? 16384 : pl.q2_rows * 128;
+        for (int idx = tid; idx < NR * 128 * 16; idx += THREADS) {
+            const int rl = idx >> 4, chunk = idx & 15;
+            const int tile = rl >> 7, row = rl & 127;
+            const int rp = rt0 * 128 + rl;
             uint4 val = make_uint4(0, 0, 0, 0);
             if (rp < R) {
                 const int i = rp / G, g = rp - i * G;
                 val = *reinterpret_cast<const uint4*>(q + (static_cast<size_t>(i) * d.n_heads + kvh * G + g) * 128 + chunk * 8);
             }
-            uint8_t* dst = smem + tile * 32768 + (chunk >> 3) * chunk_stride + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+            uint8_t* dst = smem + tile * 32768 + (chunk >> 3) * 16384 + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
             *reinterpret_cast<uint4*>(dst) = val;
         }
     }
@@ -306,24 +328,31 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
     const uint32_t tmem = *tmem_slot;
 
     constexpr int FMT = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
-    constexpr uint32_t IDESC_QK = make_idesc(128, BN, FMT, 0, 0);
+    constexpr uint32_t IDESC_QK = make_idesc(128, 64, FMT, 0, 0);
     constexpr uint32_t IDESC_PV = make_idesc(128, 128, FMT, 0, 1);
 
     if (warp == 0) {
         // ================= TMA producer (warp converged, one elected lane issues) =================
         int s = 0, ph = 0;
-        for (int j = 0; j < n_tiles; ++j) {
-            mbar_wait(bar(B_KV_EMPTY + s), ph ^ 1);
+        for (int j = 0; j < n_tiles && !LS_DBG(16); ++j) {
+            const int gi = tile_index(j);
+            const int tok = gi >= total_tiles ? sp_tiles[gi - total_tiles].tok : gi * BN;
+            const int page = __ldg(d.page_table + (tok >> 7));
+            const int row = (page * d.n_kv_heads + kvh) * LS_PAGE + (tok & (LS_PAGE - 1));
+            mbar_wait(bar(B_K_EMPTY + s), ph ^ 1);
             if (elect_one()) {
-                const int tok = j >= first_special ? sp_tiles[j - first_special].tok : (tile0 + j) * BN;
-                const int page = __ldg(d.page_table + (tok >> 7));
-                const int row = (page * d.n_kv_heads + kvh) * LS_PAGE + (tok & (LS_PAGE - 1));
-                const uint32_t dst = sbase + pl.off_kv + s * KV_STAGE_BYTES;
-                mbar_expect_tx(bar(B_KV_FULL + s), KV_STAGE_BYTES);
-                tma_load_2d(dst, &map_k, 0, row, bar(B_KV_FULL + s));
-                tma_load_2d(dst + 8192, &map_k, 64, row, bar(B_KV_FULL + s));
-                tma_load_2d(dst + 16384, &map_v, 0, row, bar(B_KV_FULL + s));
-                tma_load_2d(dst + 24576, &map_v, 64, row, bar(B_KV_FULL + s));
+                const uint32_t dst = sbase + OFF_K + s * TILE_BYTES;
+                mbar_expect_tx(bar(B_K_FULL + s), TILE_BYTES);
+                tma_load_2d(dst, &map_k, 0, row, bar(B_K_FULL + s));
+                tma_load_2d(dst + 16384, &map_k, 64, row, bar(B_K_FULL + s));
+            }
+            __syncwarp();
+            mbar_wait(bar(B_V_EMPTY + s), ph ^ 1);
+            if (elect_one()) {
+                const uint32_t dst = sbase + OFF_V + s * TILE_BYTES;
+                mbar_expect_tx(bar(B_V_FULL + s), TILE_BYTES);
+                tma_load_2d(dst, &map_v, 0, row, bar(B_V_FULL + s));
+                tma_load_2d(dst + 16384, &map_v, 64, row, bar(B_V_FULL + s));
             }
             __syncwarp();
             if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -331,111 +360,134 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
     } else if (warp == 1) {
         // ================= MMA issuer =================
         // The whole warp runs this loop converged (all values warp-uniform); one elected lane issues.
-        // Event-driven: QK(t) goes out as soon as its S buffer is free (softmax(t-2) has LOADED it) and its K tile
-        // has landed; PV(t) as soon as softmax(t) published P.  Neither waits behind the other.
+        // Steps are issued in PAIRS (pair p = steps 2p, 2p+1 = one step of each softmax warpgroup); pair p lives in
+        // S/P buffers {0,1} (p even) or {2,3} (p odd).  In-order schedule:
+        //   QK(pair 0) QK(pair 1) | P(pair 0) ready: PV(pair 0) QK(pair 2) | P(pair 1) ready: PV(pair 1) QK(pair 3) | ...
+        // MMAs of one thread execute in issue order, so QK(pair p+2) cannot overwrite the buffers PV(pair p) still
+        // reads P from.  One commit per iteration: S_FULL of pair p+2, which also certifies PV(pair p) complete.
+        // (tcgen05.mma issue is throttled to the pipe's execution rate, so every instruction the issuing thread spends
+        // on barriers is tensor-pipe idle time - hence pairs: one wait and one commit per 24 MMAs.)
         const uint32_t q_lo = (sbase >> 4) | LBO_K;
-        const uint32_t k_lo = ((sbase + pl.off_kv) >> 4) | LBO_K;
-        const uint32_t v_lo = ((sbase + pl.off_kv + 16384) >> 4) | LBO_V;
-        const uint32_t q2_chunk = (pl.q2_rows * 128) >> 4;
-        int tq = 0, rq = 0, sq = 0, phq = 0;          // next QK step: row tile, kv stage, kv_full parity
-        int tp = 0, rp = 0, sp = 0, jp0 = 1;          // next PV step: row tile, kv stage, first-tile flag
-        bool kv_ready = false;
-        while (tp < n_steps) {
-            if (tq < n_steps) {
-                const int b = tq & 1;
-                if (rq == 0 && !kv_ready) kv_ready = mbar_test(bar(B_KV_FULL + sq), phq);
-                // single S tile: QK(t) may overwrite it once softmax(t-1) (the other warpgroup) has loaded it
-                if ((rq != 0 || kv_ready) && (tq == 0 || mbar_test(bar(B_S_FREE + (b ^ 1)), ((tq - 1) >> 1) & 1))) {
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t a0 = q_lo + rq * (32768 >> 4), b0 = k_lo + sq * (KV_STAGE_BYTES >> 4);
-                        const uint32_t a_chunk = rq < 2 ? (16384u >> 4) : q2_chunk;
-                        const uint32_t dst = tmem + COL_S;
+        const uint32_t k_lo = ((sbase + OFF_K) >> 4) | LBO_K;
+        const uint32_t v_lo = ((sbase + OFF_V) >> 4) | LBO_V;
+        const int n_pairs = n_steps >> 1;
+        const int ppt = NR;                           // pairs per key tile
+        int pq = 0, iq = 0, sq = 0, phq = 0;          // next QK pair: index inside its key tile, K stage, K_FULL parity
+        int ip = 0, sp = 0, php = 0;                  // next PV pair: index inside its key tile, V stage, V_FULL parity
+        auto issue_qk_pair = [&]() {
+            if (iq == 0 && !LS_DBG(16)) mbar_wait(bar(B_K_FULL + sq), phq);
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < 8; ++kk)
-                            tc_mma2(dst, a0 + (kk >> 2) * a_chunk + (kk & 3) * 2, b0 + (kk >> 2) * (8192 >> 4) + (kk & 3) * 2,
-                                    IDESC_QK, kk > 0 ? 1u : 0u);
-                        tc_commit(bar(B_S_FULL + b));
-                    }
-                    __syncwarp();
-                    ++tq;
-                    if (++rq == NR) {
-                        rq = 0;
-                        kv_ready = false;
-                        if (++sq == STAGES) { sq = 0; phq ^= 1; }
-                    }
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const int h = NR == 2 ? iq : s2, r = NR == 2 ? s2 : 0;
+                    const uint32_t a0 = q_lo + r * (32768 >> 4), b0 = k_lo + sq * (TILE_BYTES >> 4) + h * (8192 >> 4);
+                    const uint32_t dst = tmem + COL_SP + ((2 * pq + s2) & 3) * 64;
+                    if (!LS_DBG(2))
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        tc_mma2(dst, a0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2, b0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2,
+                                IDESC_QK, kk > 0 ? 1u : 0u);
                 }
+                if (iq == ppt - 1) tc_commit(bar(B_K_EMPTY + sq));
             }
-            if (tp < tq && mbar_test(bar(B_P_FULL + (tp & 1)), (tp >> 1) & 1)) {
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t a0 = tmem + COL_P + (tp & 1) * 32, b0 = v_lo + sp * (KV_STAGE_BYTES >> 4);
-                    const uint32_t dst = tmem + COL_O + rp * 128;
+            __syncwarp();
+            ++pq;
+            if (++iq == ppt) {
+                iq = 0;
+                if (++sq == STAGES) { sq = 0; phq ^= 1; }
+            }
+        };
+        for (int i = 0; i < 2 && i < n_pairs; ++i) {
+            issue_qk_pair();
+            if (elect_one()) tc_commit(bar(B_S_FULL + i));
+            __syncwarp();
+        }
+        for (int p = 0; p < n_pairs; ++p) {
+            if (ip == 0 && !LS_DBG(16)) mbar_wait(bar(B_V_FULL + sp), php);
+            if (!LS_DBG(8)) mbar_wait(bar(B_P_FULL + (p & 1)), (p >> 1) & 1);
+            tc_fence_after();
+            if (lane == 0) LS_TRACE(0, p);
+            if (elect_one()) {
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const int h = NR == 2 ? ip : s2;
+                    const uint32_t a0 = tmem + COL_SP + ((2 * p + s2) & 3) * 64, b0 = v_lo + sp * (TILE_BYTES >> 4) + h * (8192 >> 4);
+                    const uint32_t dst = tmem + COL_O + s2 * 128;
+                    if (!LS_DBG(1))
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)      // 16 keys = 8 packed TMEM columns per K step
-                        tc_mma_ts(dst, a0 + kk * 8, b0 + kk * (2048 >> 4), IDESC_PV, (!jp0 || kk > 0) ? 1u : 0u);
-                    tc_commit(bar(B_P_FREE + (tp & 1)));
-                    tc_commit(bar(B_PV_DONE + rp));
-                    if (rp == NR - 1) tc_commit(bar(B_KV_EMPTY + sp));
+                        tc_mma_ts(dst, a0 + kk * 8, b0 + kk * (2048 >> 4), IDESC_PV, (p > 0 || kk > 0) ? 1u : 0u);
                 }
-                __syncwarp();
-                ++tp;
-                if (++rp == NR) {
-                    rp = 0;
-                    jp0 = 0;
-                    if (++sp == STAGES) sp = 0;
-                }
+                if (ip == ppt - 1) tc_commit(bar(B_V_EMPTY + sp));
             }
+            __syncwarp();
+            if (++ip == ppt) {
+                ip = 0;
+                if (++sp == STAGES) { sp = 0; php ^= 1; }
+            }
+            if (pq < n_pairs) issue_qk_pair();
+            if (elect_one()) tc_commit(bar(B_S_FULL + (p & 1)));   // S of pair p+2 is ready / PV of pair p is complete
+            __syncwarp();
+            if (lane == 0) LS_TRACE(1, p);
         }
         if (n_steps > 0 && elect_one()) tc_commit(bar(B_ALL_DONE));   // every MMA of this CTA has completed once this fires
         __syncwarp();
     } else if (warp >= 4) {
         // ================= softmax warpgroups =================
-        const int wg = (warp - 4) >> 2;                              // = step parity = S buffer = P buffer
+        const int wg = (warp - 4) >> 2;                              // = step parity = O accumulator
         const int quad = warp & 3;                                   // TMEM lane quarter of this warp
         const int row = quad * 32 + lane;                            // row inside a 128-row tile
         const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16);
         const float c2 = d.scale * 1.4426950408889634f;
         const uint64_t c2x2 = pack2(c2, c2);
-        const int b = wg;
-        int j = 0, r = wg;                                           // (key tile, row tile) of step t, kept without divisions
-        for (int t = wg; t < n_steps; t += 2, r += 2) {
-            while (r >= NR) { r -= NR; ++j; }
-            const int u = t >> 1;                                     // use count of this warpgroup's buffers
-            const bool warp_valid = r * 128 + quad * 32 < R;         // warp-uniform: any valid row in this warp
-            if (!warp_valid) {
+        const int rl = NR == 2 ? wg : 0;                             // local row tile of this warpgroup
+        const int rp0 = (rt0 + rl) * 128;                            // its first packed row
+        const bool warp_valid = rp0 + quad * 32 < R;                 // warp-uniform: any live row in this warp
+        const uint32_t o_addr = lane_addr + COL_O + wg * 128;
+        float m_ref = -INFINITY, l = 0.f;                            // this thread's row, this warpgroup's key subset
+        const int n_pairs = n_steps >> 1;
+        for (int p = 0; p < n_pairs && !LS_DBG(8); ++p) {
+            const int t = 2 * p + wg;                                // this warpgroup's step of the pair
+            const int bi = t & 3;
+            const int j = NR == 2 ? p >> 1 : p;                      // key tile
+            const int h = NR == 2 ? p & 1 : wg;                      // 64-key half of the tile
+            mbar_wait(bar(B_S_FULL + (p & 1)), (p >> 1) & 1);
+            if (!warp_valid || LS_DBG(4)) {
                 // padding rows only: keep the barrier protocol, skip the math (their O rows are never read)
-                mbar_wait(bar(B_S_FULL + b), u & 1);
-                mbar_arrive(bar(B_S_FREE + b));
-                mbar_wait(bar(B_P_FREE + b), (u & 1) ^ 1);
-                mbar_arrive(bar(B_P_FULL + b));
+                mbar_arrive(bar(B_P_FULL + (p & 1)));
                 continue;
             }
-            mbar_wait(bar(B_S_FULL + b), u & 1);
             tc_fence_after();
+            if (quad == 0 && lane == 0) LS_TRACE(2, t);
+            const uint32_t buf = lane_addr + COL_SP + bi * 64;
             uint32_t sv[64];
-            LS_TMEM_LD32(lane_addr + COL_S, sv);
-            LS_TMEM_LD32(lane_addr + COL_S + 32, (sv + 32));
+            LS_TMEM_LD32(buf, sv);
+            LS_TMEM_LD32(buf + 32, (sv + 32));
             tmem_wait_ld();
-            tc_fence_before();
-            mbar_arrive(bar(B_S_FREE + b));
-            if (j >= first_special) {
-                // per-row visibility word of this tile's 64 key slots
-                const SpecialTile st = sp_tiles[j - first_special];
-                const int rp = r * 128 + row;
+            if (quad == 0 && lane == 0) LS_TRACE(3, t);
+            const int gi = tile_index(j);
+            if (gi >= total_tiles) {
+                // per-row visibility word of this half's 64 key slots
+                const SpecialTile st = sp_tiles[gi - total_tiles];
+                const int rp = rp0 + row;
                 uint64_t vis = 0ull;
                 if (rp < R) {
                     const int qi = rp / G;
                     if (st.kind == 0) {
-                        const int hi = d.causal ? kv_len - (n_q - 1 - qi) : kv_len;      // visible global keys: j < hi
-                        const int cnt = min(max(hi - st.base, 0), st.n_valid);
-                        vis = cnt >= 64 ? ~0ull : ((1ull << cnt) - 1ull);
+                        const int hi = d.causal ? kv_len - (n_q - 1 - qi) : kv_len;      // visible global keys: key < hi
+                        const int cnt = min(max(hi - st.base, 0), st.n_valid) - h * 64;
+                        vis = cnt >= 64 ? ~0ull : (cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull));
                     } else {
                         const uint64_t* w = d.tail_mask + static_cast<size_t>(qi) * LS_MASK_WORDS;
-                        const int wi = st.base >> 6, sh = st.base & 63;
-                        vis = w[wi] >> sh;
-                        if (sh && wi + 1 < LS_MASK_WORDS) vis |= w[wi + 1] << (64 - sh);
-                        if (st.n_valid < 64) vis &= (1ull << st.n_valid) - 1ull;
+                        const int k0 = st.base + h * 64;
+                        const int wi = k0 >> 6, sh = k0 & 63;
+                        if (wi < LS_MASK_WORDS) {
+                            vis = w[wi] >> sh;
+                            if (sh && wi + 1 < LS_MASK_WORDS) vis |= w[wi + 1] << (64 - sh);
+                        }
+                        const int cnt = st.n_valid - h * 64;
+                        if (cnt < 64) vis &= cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull);
                     }
                 }
 #pragma unroll
@@ -451,42 +503,32 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                 mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sv[e + 6]), __uint_as_float(sv[e + 7])));
             }
             const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c2;
-            // The row state of (r, j-1) was written by the OTHER warpgroup when NR is odd.  Hand it over through a
-            // per-row version counter (release/acquire in shared memory): exact, and free of mbarrier aliasing.
-            {
-                const uint32_t va = smem_u32(st_ver + r * 128 + row);
-                uint32_t ver;
-                do {
-                    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(ver) : "r"(va) : "memory");
-                } while (ver != static_cast<uint32_t>(j));
-            }
-            float m_ref = st_m[r * 128 + row], l = st_l[r * 128 + row];
             const bool need = mx > m_ref + 8.0f;                     // lazy rescale threshold (2^8)
             if (__any_sync(0xffffffffu, need)) {
                 const float m_new = need ? mx : m_ref;
-                const float alpha = fast_exp2(m_ref - m_new);        // -inf - x -> 0 on the first tile
+                const float alpha = fast_exp2(m_ref - m_new);        // -inf - x -> 0 on the first step
                 l *= alpha;
                 m_ref = m_new;
-                if (j > 0) {
-                    // O_r is quiescent once PV(r, j-1) completed.  First make sure PV(t-2) is complete (our own
-                    // P_FREE phase) so that PV_DONE[r] is at most one phase behind and the parity wait cannot alias.
-                    mbar_wait(bar(B_P_FREE + b), (u & 1) ^ 1);
-                    mbar_wait(bar(B_PV_DONE + r), (j - 1) & 1);
+                if (p >= 1) {
+                    // This accumulator is quiescent once PV(pair p-1) completed, which the commit of iteration p-1 - the
+                    // S_FULL of pair p+1, this warpgroup's next wait anyway - certifies.  That barrier's previous phase
+                    // (pair p-1) completed long ago, so the parity wait cannot alias.
+                    mbar_wait(bar(B_S_FULL + ((p + 1) & 1)), ((p + 1) >> 1) & 1);
                     tc_fence_after();
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         uint32_t ov[32];
-                        LS_TMEM_LD32(lane_addr + COL_O + r * 128 + c * 32, ov);
+                        LS_TMEM_LD32(o_addr + c * 32, ov);
                         tmem_wait_ld();
 #pragma unroll
                         for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
-                        LS_TMEM_ST32(lane_addr + COL_O + r * 128 + c * 32, ov);
+                        LS_TMEM_ST32(o_addr + c * 32, ov);
                     }
                     tmem_wait_st();
                     tc_fence_before();
                 }
             }
-            // p = 2^(s * c2 - m_ref), packed fp32x2 FMA / ADD, four independent partial sums
+            // p = 2^(s * c2 - m_ref), packed fp32x2 FMA / ADD
             const float m_use = m_ref == -INFINITY ? 0.f : m_ref;      // row with no visible key so far: p = 2^(-inf) = 0
             const uint64_t negm = pack2(-m_use, -m_use);
             uint64_t sum_a = 0ull, sum_b = 0ull;                     // {0.f, 0.f}
@@ -503,47 +545,39 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                 pk[(e >> 1) + 1] = Num<T>::pack(p2, p3);
             }
             {
-                float a0, a1, b0, b1;
+                float a0, a1;
                 unpack2(add2(sum_a, sum_b), a0, a1);
-                (void)b0; (void)b1;
                 l += a0 + a1;
             }
-            st_m[r * 128 + row] = m_ref;
-            st_l[r * 128 + row] = l;
-            asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(st_ver + r * 128 + row)), "r"(static_cast<uint32_t>(j + 1)) : "memory");
-            // P tile -> this warpgroup's TMEM buffer (A operand of the PV MMA, 2 values per 32-bit column);
-            // PV(t-2) must be done with it
-            mbar_wait(bar(B_P_FREE + b), (u & 1) ^ 1);
-            tc_fence_after();
-            LS_TMEM_ST32(lane_addr + COL_P + b * 32, pk);
+            // P -> in place over the S tile it came from (A operand of the PV MMA, 2 values per 32-bit column)
+            if (quad == 0 && lane == 0) LS_TRACE(4, t);
+            LS_TMEM_ST32(buf, pk);
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(bar(B_P_FULL + b));
+            mbar_arrive(bar(B_P_FULL + (p & 1)));
+            if (quad == 0 && lane == 0) LS_TRACE(5, t);
         }
         // ================= epilogue: normalised partial O + LSE =================
         const int Rtot = d.q_rows * G;
-        const int part = d.part_offset + split;
-        for (int re = wg; re < NR; re += 2) {
-            const int rp = re * 128 + row;
-            if (n_tiles > 0) {
-                mbar_wait(bar(B_ALL_DONE), 0);       // single-phase barrier: no parity aliasing
-                tc_fence_after();
-            }
-            const float l = st_l[rp], m_ref = st_m[rp];
-            const float inv = (n_tiles > 0 && l > 0.f) ? 1.f / l : 0.f;
-            const size_t base = (static_cast<size_t>(part) * d.n_kv_heads + kvh) * Rtot + rp;
+        const int part = d.part_offset + slot;
+        const int nr_out = min(NRS - rt0, NRL_MAX);                 // row tiles this CTA is responsible for
+        if (n_steps > 0) {
+            mbar_wait(bar(B_ALL_DONE), 0);           // single-phase barrier: no parity aliasing
+            tc_fence_after();
+        }
+        auto part_base = [&](int sl, int rp) { return (static_cast<size_t>(d.part_offset + sl) * d.n_kv_heads + kvh) * Rtot + rp; };
+        if (NR == 2) {
+            // warpgroup = row tile: (m_ref, l) and the accumulator are complete as they stand
+            const int rp = rp0 + row;
+            const float inv = l > 0.f ? 1.f / l : 0.f;
+            const size_t base = part_base(slot, rp);
             if (rp < R) d.part_lse[base] = inv > 0.f ? (m_ref + log2f(l)) * 0.6931471805599453f : -INFINITY;
-            if (re * 128 + quad * 32 < R) {               // warp-uniform (tcgen05.ld is warp-collective)
+            if (warp_valid) {                             // warp-uniform (tcgen05.ld is warp-collective)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t ov[32];
-                    if (n_tiles > 0) {
-                        LS_TMEM_LD32(lane_addr + COL_O + re * 128 + c * 32, ov);
-                        tmem_wait_ld();
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) ov[e] = 0u;
-                    }
+                    LS_TMEM_LD32(o_addr + c * 32, ov);
+                    tmem_wait_ld();
                     if (rp < R) {
                         float* po = d.part_o + base * 128 + c * 32;
 #pragma unroll
@@ -551,6 +585,59 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                             *reinterpret_cast<float4*>(po + e) =
                                 make_float4(__uint_as_float(ov[e]) * inv, __uint_as_float(ov[e + 1]) * inv,
                                             __uint_as_float(ov[e + 2]) * inv, __uint_as_float(ov[e + 3]) * inv);
+                    }
+                }
+            }
+        } else {
+            // One (or no) live row tile: the two warpgroups hold partial states of the SAME rows over alternate key
+            // halves.  Exchange (m, l) through shared memory, then each warpgroup merges and writes 64 of the 128
+            // output columns.  Row tiles without live rows / CTAs without keys write empty partials.
+            st_m[wg * 128 + row] = m_ref;
+            st_l[wg * 128 + row] = l;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float m0 = st_m[row], m1 = st_m[128 + row], l0 = st_l[row], l1 = st_l[128 + row];
+            const float m = fmaxf(m0, m1);
+            const float a0 = l0 > 0.f ? fast_exp2(m0 - m) : 0.f, a1 = l1 > 0.f ? fast_exp2(m1 - m) : 0.f;
+            const float lt = l0 * a0 + l1 * a1;
+            const float inv = lt > 0.f ? 1.f / lt : 0.f;
+            const float w0 = a0 * inv, w1 = a1 * inv;
+            for (int re = 0; re < nr_out; ++re) {
+                const bool live = re == 0 && NR == 1 && n_steps > 0;
+                const int rp = (rt0 + re) * 128 + row;
+                const size_t base = part_base(slot, rp);
+                if (wg == 0 && rp < R) {
+                    d.part_lse[base] = (live && inv > 0.f) ? (m + log2f(lt)) * 0.6931471805599453f : -INFINITY;
+                    if (empty_slot >= 0) d.part_lse[part_base(empty_slot, rp)] = -INFINITY;
+                }
+                if ((rt0 + re) * 128 + quad * 32 < R) {   // warp-uniform
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int col = wg * 64 + c * 32;
+                        uint32_t o0[32], o1[32];
+                        if (live) {
+                            LS_TMEM_LD32(lane_addr + COL_O + col, o0);
+                            LS_TMEM_LD32(lane_addr + COL_O + 128 + col, o1);
+                            tmem_wait_ld();
+                        }
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            // an accumulator that never received a PV holds stale TMEM bits: select, do not multiply
+                            const float x0 = (live && w0 > 0.f) ? __uint_as_float(o0[e]) * w0 : 0.f;
+                            const float x1 = (live && w1 > 0.f) ? __uint_as_float(o1[e]) * w1 : 0.f;
+                            o0[e] = __float_as_uint(x0 + x1);
+                        }
+                        if (rp < R) {
+                            float* po = d.part_o + base * 128 + col;
+#pragma unroll
+                            for (int e = 0; e < 32; e += 4)
+                                *reinterpret_cast<float4*>(po + e) = make_float4(__uint_as_float(o0[e]), __uint_as_float(o0[e + 1]),
+                                                                                __uint_as_float(o0[e + 2]), __uint_as_float(o0[e + 3]));
+                            if (empty_slot >= 0) {
+                                float* pe = d.part_o + part_base(empty_slot, rp) * 128 + col;
+#pragma unroll
+                                for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(pe + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                        }
                     }
                 }
             }
@@ -600,7 +687,7 @@ static int get_map(const void* pool, long long rows, int dtype, CUtensorMap* out
     CUtensorMap m;
     cuuint64_t gdim[2] = {128, static_cast<cuuint64_t>(rows)};
     cuuint64_t gstride[1] = {256};
-    cuuint32_t box[2] = {64, 64};
+    cuuint32_t box[2] = {64, 128};
     cuuint32_t estr[2] = {1, 1};
     CUresult rc = fn(&m, dtype == LS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                      const_cast<void*>(pool), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -614,9 +701,11 @@ static int get_map(const void* pool, long long rows, int dtype, CUtensorMap* out
 }  // namespace tc
 }  // namespace ls
 
-// Launch the tensor-core kernel over the unmasked full tiles with `n_splits_tc` splits writing partial slots
+// Launch the tensor-core kernel over the unmasked full tiles, writing partial slots
 // [part_offset, part_offset + n_splits_tc).  With `fuse_remainder` the masked remainder (partial tile, causal
 // rows, tree-masked tail) is appended to the tile sequence as special tiles and shared out with the rest.
+// Up to two row tiles: one CTA per (slot, kv head).  Three row tiles: two heavy CTAs per pair of slots plus
+// one light CTA (see the header comment): grid.x = n_slots + ceil(n_slots / 2).
 static int launch_tc(const ls_attn_desc* d, int n_splits_tc, int fuse_remainder, void* stream) {
     using namespace ls;
     using namespace ls::tc;
@@ -637,7 +726,8 @@ static int launch_tc(const ls_attn_desc* d, int n_splits_tc, int fuse_remainder,
         cudaFuncSetAttribute(attn_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         attr_set = true;
     }
-    dim3 grid(n_splits_tc, d->n_kv_heads);
+    const int nrs = (d->q_rows * G + 127) / 128;
+    dim3 grid(nrs > NRL_MAX ? n_splits_tc + (n_splits_tc + 1) / 2 : n_splits_tc, d->n_kv_heads);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (d->dtype == LS_F16)
         attn_tc_kernel<__half><<<grid, THREADS, SMEM_BYTES, st>>>(*d, mk, mv, n_splits_tc, fuse_remainder);
@@ -645,6 +735,16 @@ static int launch_tc(const ls_attn_desc* d, int n_splits_tc, int fuse_remainder,
         attn_tc_kernel<__nv_bfloat16><<<grid, THREADS, SMEM_BYTES, st>>>(*d, mk, mv, n_splits_tc, fuse_remainder);
     return check_launch("ls_attn_partial_tc");
 }
+
+#ifdef LS_TC_TRACE
+extern "C" int ls_debug_set_flags(int flags) {
+    return cudaMemcpyToSymbol(ls::tc::g_dbg, &flags, sizeof(flags)) == cudaSuccess ? LS_OK : LS_ERR_CUDA;
+}
+extern "C" int ls_debug_set_trace(void* buf) {
+    long long* p = static_cast<long long*>(buf);
+    return cudaMemcpyToSymbol(ls::tc::g_trace, &p, sizeof(p)) == cudaSuccess ? LS_OK : LS_ERR_CUDA;
+}
+#endif
 
 extern "C" int ls_attn_partial_tc(const ls_attn_desc* d, int n_splits_tc, void* stream) { return launch_tc(d, n_splits_tc, 0, stream); }
 // the whole call in one launch: d->n_splits CTAs per kv head share the unmasked and the special tiles

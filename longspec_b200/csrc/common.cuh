@@ -75,12 +75,12 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// Number of full, unmasked 64-key tiles of the LOCAL prefix covered by the tensor-core kernel (attn_tc.cu);
+// Number of full, unmasked 128-key tiles of the LOCAL prefix covered by the tensor-core kernel (attn_tc.cu);
 // the masked remainder on the mma.sync path starts at this tile.  Shared so both kernels agree.
 __device__ __forceinline__ int tc_full_tiles(const ls_attn_desc& d, int kv_len, int n_q) {
     const int se = d.kv_shard_end < 0 ? 0x7fffffff : d.kv_shard_end;
     const int end = min(kv_len - (d.causal ? n_q : 0), se) - d.kv_shard_begin;
-    return max(end, 0) / 64;
+    return max(end, 0) / 128;
 }
 
 }  // namespace ls

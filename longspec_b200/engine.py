@@ -247,9 +247,14 @@ class Engine:
 
         def splits(rows):
             if rows * G <= 384:
-                # tcgen05 path: one CTA per SM over (split, kv head); the masked remainder rides along as special
-                # tiles.  Short contexts take fewer splits (>= 8 tiles per CTA) to keep the partial traffic down.
-                return int(max(1, min(self.sms // d.kv_heads, (tiles + 7) // 8)))
+                # tcgen05 path, one CTA per SM.  Up to two row tiles of 128 packed rows: (slot, kv head) CTAs.  Three
+                # row tiles: trios of two heavy CTAs (two slots) + one light CTA, i.e. 1.5 CTAs per slot.  Short
+                # contexts take fewer slots (>= 4 tiles of 128 keys per share) to keep the partial traffic down.
+                tiles128 = (tiles + 1) // 2
+                if rows * G <= 256:
+                    return int(max(1, min(self.sms // d.kv_heads, (tiles128 + 3) // 4)))
+                groups = max(1, min(self.sms // (3 * d.kv_heads), (tiles128 + 7) // 8))
+                return int(2 * groups)
             rb = (rows * G + 127) // 128
             return int(max(1, min(tiles, math.ceil(2 * self.sms / (d.kv_heads * rb)), 64)))
         self.n_split_verify = splits(self.q_v)

@@ -28,7 +28,7 @@ q = torch.randn(qv, H, 128, generator=g, device=dev, dtype=torch.float32).to(dt)
 out = torch.empty_like(q)
 G = H // Hk
 sms = _lib.load().ls_sm_count()
-n_splits = int(os.environ.get("SPLITS", sms // Hk))
+n_splits = int(os.environ.get("SPLITS", sms // Hk if qv * G <= 256 else 2 * (sms // (3 * Hk))))
 part_o = torch.empty(n_splits * Hk * qv * G * 128, dtype=torch.float32, device=dev)
 part_l = torch.empty(n_splits * Hk * qv * G, dtype=torch.float32, device=dev)
 kvl = torch.tensor([N], dtype=torch.int32, device=dev)
