@@ -314,8 +314,12 @@ def main():
     alg_flops = 4.0 * int(eng.p_veri_rows) * local_keys * 128 * d.heads
     peak, peak_src = peaks()
     achieved = alg_bytes / (attn_ms * 1e-3) / 1e9
+    traffic = None                           # dram bytes per launch from the committed ncu --set full capture (same shape only)
+    tp = os.path.join(ROOT, "profiles", "attn_tc_traffic.json")
+    if os.path.exists(tp) and world == 1 and PROMPT == 131072 and MODEL == "llama3-8b-262k":
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     roofline = {"kernel": "ls_attn_partial (target tree-verify attention, one layer)", "bound": "hbm",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "us_per_launch": attn_ms * 1e3, "algorithmic_bytes": alg_bytes,
                 "tensor_tflops": alg_flops / (attn_ms * 1e-3) / 1e12,
                 "share_of_round": attn_ms * d.layers / (ms / K)}

@@ -86,6 +86,18 @@ def full(rep_name="attn_tc_full"):
         for i, h in enumerate(hdr):
             if h in KEYS or h == "Kernel Name":
                 f.write(f"{h} [{units[i]}]: " + " | ".join(r[i][:70] for r in data) + "\n")
+        try:   # dram bytes per launch of the dominant kernel -> bench.py's roofline.traffic
+            import json
+            col = {h: i for i, h in enumerate(hdr)}
+            scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+            tot = 0.0
+            for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(data[-1][col[name]].replace(",", "")) * scale[units[col[name]]]
+            json.dump({"kernel": "attn_tc_kernel", "workload": "llama3-8b verify shape, 131072 keys, one layer call",
+                       "dram_bytes_per_launch": tot, "source": f"profiles/{tag}_{rep_name}_summary.txt"},
+                      open(os.path.join(PROF, "attn_tc_traffic.json"), "w"))
+        except Exception as e:  # noqa: BLE001
+            print("traffic json not written:", e)
         src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
         rs = list(csv.reader(src.splitlines()))
         his = [i for i, r in enumerate(rs) if r and r[0] == "Address"]
