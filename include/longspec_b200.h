@@ -73,7 +73,7 @@ int ls_sm_count(void);
  * online softmax; results agree within the tolerance stated in tests/test_attention_gpu.py.
  * ---------------------------------------------------------------------------------------- */
 typedef struct ls_attn_desc {
-    const void* q;              /* [q_rows][n_heads][128] dtype, post-RoPE */
+    const void* q;              /* [q_rows][n_heads][128] dtype, post-RoPE; row stride q_stride */
     void* out;                  /* [q_rows][n_heads][128] dtype */
     const void* k_pool;         /* paged pool, see above */
     const void* v_pool;
@@ -99,6 +99,8 @@ typedef struct ls_attn_desc {
     int32_t kv_shard_end;       /*   global sequence; page_table indexes LOCAL pages; -1 = unbounded */
     int32_t tail_owner;         /* 1 if this GPU processes the tail keys (exactly one rank does) */
     float scale;                /* softmax scale, 1/sqrt(128) */
+    int64_t q_stride;           /* elements between consecutive query rows of `q` (0 = dense, n_heads * 128): lets the
+                                   q slice of a fused QKV GEMM output be read in place */
 } ls_attn_desc;
 
 /* split-KV partial pass: writes (normalised O, LSE) per (split, kv head, row) into the workspace */

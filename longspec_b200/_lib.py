@@ -26,7 +26,7 @@ class AttnDesc(C.Structure):
         ("kv_len_bias", i32), ("q_rows", i32), ("n_heads", i32), ("n_kv_heads", i32), ("n_tail", i32),
         ("window", i32), ("causal", i32), ("dtype", i32), ("n_splits", i32), ("n_pages", i32),
         ("part_offset", i32), ("n_parts_total", i32), ("kv_shard_begin", i32), ("kv_shard_end", i32),
-        ("tail_owner", i32), ("scale", f32),
+        ("tail_owner", i32), ("scale", f32), ("q_stride", i64),
     ]
 
 

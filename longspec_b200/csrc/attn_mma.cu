@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) attn_partial_kernel(const ls_a
 
     // ---- stage Q (this CTA's 128 packed rows) through shared memory into A fragments -------------
     const T* __restrict__ q = reinterpret_cast<const T*>(d.q);
+    const size_t q_stride = d.q_stride > 0 ? static_cast<size_t>(d.q_stride) : static_cast<size_t>(d.n_heads) * 128;
     {
         uint8_t* qs = smem;   // 32 KB, reuses stage 0/1 space before the pipeline starts
 #pragma unroll
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) attn_partial_kernel(const ls_a
             uint4 val = make_uint4(0, 0, 0, 0);
             if (r < R) {
                 const int i = r / G, g = r - i * G;
-                val = *reinterpret_cast<const uint4*>(q + (static_cast<size_t>(i) * d.n_heads + kvh * G + g) * kD + chunk * 8);
+                val = *reinterpret_cast<const uint4*>(q + static_cast<size_t>(i) * q_stride + static_cast<size_t>(kvh * G + g) * kD + chunk * 8);
             }
             *reinterpret_cast<uint4*>(qs + swz(row, chunk)) = val;
         }
@@ -393,6 +394,8 @@ static int validate(const ls_attn_desc* d) {
     LS_REQUIRE(d->n_tail >= 0 && d->n_tail <= 64 * LS_MASK_WORDS, "ls_attn: n_tail %d out of range", d->n_tail);
     LS_REQUIRE(d->n_tail == 0 || d->tail_mask != nullptr, "ls_attn: n_tail > 0 needs tail_mask");
     LS_REQUIRE(d->dtype == LS_F16 || d->dtype == LS_BF16, "ls_attn: bad dtype %d", d->dtype);
+    LS_REQUIRE(d->q_stride == 0 || (d->q_stride >= static_cast<int64_t>(d->n_heads) * 128 && d->q_stride % 8 == 0),
+               "ls_attn: q_stride %lld must be 0 or >= n_heads * 128 and a multiple of 8 elements", static_cast<long long>(d->q_stride));
     LS_REQUIRE(d->n_splits >= 1 && d->part_offset >= 0 && d->part_offset + d->n_splits <= d->n_parts_total,
                "ls_attn: bad split/part configuration (%d splits, offset %d, total %d)", d->n_splits, d->part_offset,
                d->n_parts_total);

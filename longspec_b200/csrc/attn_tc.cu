@@ -308,6 +308,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
     // Q tiles -> swizzled shared memory (K-major, SWIZZLE_128B): [tile][k-chunk][row][128B]
     if (n_steps > 0) {
         const T* __restrict__ q = reinterpret_cast<const T*>(d.q);
+        const size_t q_stride = d.q_stride > 0 ? static_cast<size_t>(d.q_stride) : static_cast<size_t>(d.n_heads) * 128;
         for (int idx = tid; idx < NR * 128 * 16; idx += THREADS) {
             const int rl = idx >> 4, chunk = idx & 15;
             const int tile = rl >> 7, row = rl & 127;
@@ -315,7 +316,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
             uint4 val = make_uint4(0, 0, 0, 0);
             if (rp < R) {
                 const int i = rp / G, g = rp - i * G;
-                val = *reinterpret_cast<const uint4*>(q + (static_cast<size_t>(i) * d.n_heads + kvh * G + g) * 128 + chunk * 8);
+                val = *reinterpret_cast<const uint4*>(q + static_cast<size_t>(i) * q_stride + static_cast<size_t>(kvh * G + g) * 128 + chunk * 8);
             }
             uint8_t* dst = smem + tile * 32768 + (chunk >> 3) * 16384 + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
             *reinterpret_cast<uint4*>(dst) = val;
@@ -374,24 +375,22 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         const int ppt = NR;                           // pairs per key tile
         int pq = 0, iq = 0, sq = 0, phq = 0;          // next QK pair: index inside its key tile, K stage, K_FULL parity
         int ip = 0, sp = 0, php = 0;                  // next PV pair: index inside its key tile, V stage, V_FULL parity
-        auto issue_qk_pair = [&]() {
-            if (iq == 0 && !LS_DBG(16)) mbar_wait(bar(B_K_FULL + sq), phq);
-            tc_fence_after();
-            if (elect_one()) {
+        // QK MMAs of pair pq (elected lane only) / bookkeeping of the QK cursor (whole warp)
+        auto qk_pair_mmas = [&]() {
 #pragma unroll
-                for (int s2 = 0; s2 < 2; ++s2) {
-                    const int h = NR == 2 ? iq : s2, r = NR == 2 ? s2 : 0;
-                    const uint32_t a0 = q_lo + r * (32768 >> 4), b0 = k_lo + sq * (TILE_BYTES >> 4) + h * (8192 >> 4);
-                    const uint32_t dst = tmem + COL_SP + ((2 * pq + s2) & 3) * 64;
-                    if (!LS_DBG(2))
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const int h = NR == 2 ? iq : s2, r = NR == 2 ? s2 : 0;
+                const uint32_t a0 = q_lo + r * (32768 >> 4), b0 = k_lo + sq * (TILE_BYTES >> 4) + h * (8192 >> 4);
+                const uint32_t dst = tmem + COL_SP + ((2 * pq + s2) & 3) * 64;
+                if (!LS_DBG(2))
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)
-                        tc_mma2(dst, a0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2, b0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2,
-                                IDESC_QK, kk > 0 ? 1u : 0u);
-                }
-                if (iq == ppt - 1) tc_commit(bar(B_K_EMPTY + sq));
+                for (int kk = 0; kk < 8; ++kk)
+                    tc_mma2(dst, a0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2, b0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2,
+                            IDESC_QK, kk > 0 ? 1u : 0u);
             }
-            __syncwarp();
+            if (iq == ppt - 1) tc_commit(bar(B_K_EMPTY + sq));
+        };
+        auto qk_advance = [&]() {
             ++pq;
             if (++iq == ppt) {
                 iq = 0;
@@ -399,12 +398,20 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
             }
         };
         for (int i = 0; i < 2 && i < n_pairs; ++i) {
-            issue_qk_pair();
-            if (elect_one()) tc_commit(bar(B_S_FULL + i));
+            if (iq == 0 && !LS_DBG(16)) mbar_wait(bar(B_K_FULL + sq), phq);
+            tc_fence_after();
+            if (elect_one()) {
+                qk_pair_mmas();
+                tc_commit(bar(B_S_FULL + i));
+            }
             __syncwarp();
+            qk_advance();
         }
         for (int p = 0; p < n_pairs; ++p) {
+            // all waits first, then ONE elected block issues PV(pair p), QK(pair p+2) and the commits back to back
+            const bool do_qk = pq < n_pairs;
             if (ip == 0 && !LS_DBG(16)) mbar_wait(bar(B_V_FULL + sp), php);
+            if (do_qk && iq == 0 && !LS_DBG(16)) mbar_wait(bar(B_K_FULL + sq), phq);
             if (!LS_DBG(8)) mbar_wait(bar(B_P_FULL + (p & 1)), (p >> 1) & 1);
             tc_fence_after();
             if (lane == 0) LS_TRACE(0, p);
@@ -420,15 +427,15 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                         tc_mma_ts(dst, a0 + kk * 8, b0 + kk * (2048 >> 4), IDESC_PV, (p > 0 || kk > 0) ? 1u : 0u);
                 }
                 if (ip == ppt - 1) tc_commit(bar(B_V_EMPTY + sp));
+                if (do_qk) qk_pair_mmas();
+                tc_commit(bar(B_S_FULL + (p & 1)));      // S of pair p+2 is ready / PV of pair p is complete
             }
             __syncwarp();
             if (++ip == ppt) {
                 ip = 0;
                 if (++sp == STAGES) { sp = 0; php ^= 1; }
             }
-            if (pq < n_pairs) issue_qk_pair();
-            if (elect_one()) tc_commit(bar(B_S_FULL + (p & 1)));   // S of pair p+2 is ready / PV of pair p is complete
-            __syncwarp();
+            if (do_qk) qk_advance();
             if (lane == 0) LS_TRACE(1, p);
         }
         if (n_steps > 0 && elect_one()) tc_commit(bar(B_ALL_DONE));   // every MMA of this CTA has completed once this fires
@@ -559,7 +566,6 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         }
         // ================= epilogue: normalised partial O + LSE =================
         const int Rtot = d.q_rows * G;
-        const int part = d.part_offset + slot;
         const int nr_out = min(NRS - rt0, NRL_MAX);                 // row tiles this CTA is responsible for
         if (n_steps > 0) {
             mbar_wait(bar(B_ALL_DONE), 0);           // single-phase barrier: no parity aliasing
@@ -576,8 +582,14 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t ov[32];
-                    LS_TMEM_LD32(o_addr + c * 32, ov);
-                    tmem_wait_ld();
+                    if (n_steps > 0) {
+                        LS_TMEM_LD32(o_addr + c * 32, ov);
+                        tmem_wait_ld();
+                    }
+                    if (inv == 0.f) {                     // no key seen (or no tile at all): the accumulator holds stale bits
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) ov[e] = 0u;
+                    }
                     if (rp < R) {
                         float* po = d.part_o + base * 128 + c * 32;
 #pragma unroll
@@ -714,6 +726,9 @@ static int launch_tc(const ls_attn_desc* d, int n_splits_tc, int fuse_remainder,
     LS_REQUIRE(d->q_rows * G <= NR_MAX * 128, "ls_attn_partial_tc: %d packed rows exceed %d", d->q_rows * G, NR_MAX * 128);
     LS_REQUIRE(d->window < 0, "ls_attn_partial_tc: windowed attention stays on the general path");
     LS_REQUIRE(d->n_pages > 0, "ls_attn_partial_tc: n_pages must be set");
+    LS_REQUIRE(d->q_stride == 0 || (d->q_stride >= static_cast<int64_t>(d->n_heads) * 128 && d->q_stride % 8 == 0),
+               "ls_attn_partial_tc: q_stride %lld must be 0 or >= n_heads * 128 and a multiple of 8 elements",
+               static_cast<long long>(d->q_stride));
     CUtensorMap mk, mv;
     const long long rows = static_cast<long long>(d->n_pages) * d->n_kv_heads * LS_PAGE;
     int rc = get_map(d->k_pool, rows, d->dtype, &mk);

@@ -66,6 +66,34 @@ class Shard:
         return Shard(rank, world, begin, end)
 
 
+def split_plan(heads, kv_heads, sms, prompt_len, total_tokens, world, row_counts):
+    """Partial slots per attention call for each query-row count in `row_counts`.
+
+    Every rank must plan the SAME number of slots (the exchange all-gathers equal-sized blocks and the combine
+    reads world * n_splits of them), so the plan is made for the LARGEST shard - which every rank can compute."""
+    G = heads // kv_heads
+
+    def shard_tokens(s):
+        n = (total_tokens - s.begin) if s.end < 0 else (s.end - s.begin)
+        return (max(n, LS_PAGE) + LS_PAGE - 1) // LS_PAGE * LS_PAGE
+    max_local = max(shard_tokens(Shard.make(prompt_len, r, world)) for r in range(world))
+    tiles = max((max_local + 63) // 64, 1)
+
+    def splits(rows):
+        if rows * G <= 384:
+            # tcgen05 path, one CTA per SM.  Up to two row tiles of 128 packed rows: (slot, kv head) CTAs.  Three
+            # row tiles: trios of two heavy CTAs (two slots) + one light CTA, i.e. 1.5 CTAs per slot.  Short
+            # contexts take fewer slots (>= 4 tiles of 128 keys per share) to keep the partial traffic down.
+            tiles128 = (tiles + 1) // 2
+            if rows * G <= 256:
+                return int(max(1, min(sms // kv_heads, (tiles128 + 3) // 4)))
+            groups = max(1, min(sms // (3 * kv_heads), (tiles128 + 7) // 8))
+            return int(2 * groups)
+        rb = (rows * G + 127) // 128
+        return int(max(1, min(tiles, math.ceil(2 * sms / (kv_heads * rb)), 64)))
+    return tuple(splits(r) for r in row_counts)
+
+
 class PagedKV:
     """Paged K/V pools: pool[layer] = (K, V), each [n_pages][Hk][128][128]; one page table."""
 
@@ -242,24 +270,8 @@ class Engine:
 
         # split-KV plan (static grids; each split's key range adapts to the device-side lengths)
         G = d.heads // d.kv_heads
-        max_local = self.kv.max_tokens
-        tiles = max((max_local + 63) // 64, 1)
-
-        def splits(rows):
-            if rows * G <= 384:
-                # tcgen05 path, one CTA per SM.  Up to two row tiles of 128 packed rows: (slot, kv head) CTAs.  Three
-                # row tiles: trios of two heavy CTAs (two slots) + one light CTA, i.e. 1.5 CTAs per slot.  Short
-                # contexts take fewer slots (>= 4 tiles of 128 keys per share) to keep the partial traffic down.
-                tiles128 = (tiles + 1) // 2
-                if rows * G <= 256:
-                    return int(max(1, min(self.sms // d.kv_heads, (tiles128 + 3) // 4)))
-                groups = max(1, min(self.sms // (3 * d.kv_heads), (tiles128 + 7) // 8))
-                return int(2 * groups)
-            rb = (rows * G + 127) // 128
-            return int(max(1, min(tiles, math.ceil(2 * self.sms / (d.kv_heads * rb)), 64)))
-        self.n_split_verify = splits(self.q_v)
-        self.n_split_cross = splits(n_step)
-        self.n_split_one = splits(1)
+        plan = split_plan(d.heads, d.kv_heads, self.sms, prompt_len, total, sh.world, (self.q_v, n_step, 1))
+        self.n_split_verify, self.n_split_cross, self.n_split_one = plan
         self.n_split_self = 4
         world = sh.world
         max_parts = max(self.n_split_verify, self.n_split_cross, self.n_split_one) * world
@@ -288,6 +300,7 @@ class Engine:
         a.part_offset, a.n_parts_total = sh.rank * n_splits, sh.world * n_splits
         a.kv_shard_begin, a.kv_shard_end, a.tail_owner = sh.begin, sh.end, int(sh.owner)
         a.scale = self.scale
+        a.q_stride = q.stride(0)             # the q slice of a fused QKV output is read in place
         return a
 
     def _attn(self, q, out, pools, layer, kv_len_ptr, n_q_ptr, q_rows, n_splits, **kw):
@@ -361,9 +374,8 @@ class Engine:
             q, k, v = qkv[:, :HD], qkv[:, HD:HD + KD], qkv[:, HD + KD:]
             self._rope_append(q, k, v, qkv.stride(0), qkv.stride(0), positions, self.kv if sh.owner else None, li,
                               kv_len_ptr, kv_len_bias - sh.begin, 0, n_rows_ptr, rows)
-            qc = q.contiguous()
             attn = torch.empty(rows, HD, dtype=self.dtype, device=self.device)
-            self._attn(qc, attn, self.kv, li, kv_len_ptr, n_rows_ptr, rows, n_splits, kv_len_bias=kv_len_bias,
+            self._attn(q, attn, self.kv, li, kv_len_ptr, n_rows_ptr, rows, n_splits, kv_len_bias=kv_len_bias,
                        n_tail=n_tail, tail_mask=tail_mask, causal=causal)
             o = F.linear(attn, L["o"])
             x = self._norm(h, o, L["ln2"])
@@ -424,7 +436,7 @@ class Engine:
         self._rope_append(q, k, v, qkv.stride(0), qkv.stride(0), st["step_pos"], self.dkv, 0, self.p_draft_len,
                           0, slot_off, self.p_step_rows, rows)
         attn = torch.empty(rows, HD, dtype=self.dtype, device=self.device)
-        self._attn(q.contiguous(), attn, self.dkv, 0, self_kv_ptr, self.p_step_rows, rows, self.n_split_self,
+        self._attn(q, attn, self.dkv, 0, self_kv_ptr, self.p_step_rows, rows, self.n_split_self,
                    kv_len_bias=self_bias, n_tail=n_tail, tail_mask=mask, window=512, causal=causal, sharded=False)
         o = F.linear(attn, D["sa_o"])
         # --- cross attention over the target's last-layer KV

@@ -40,7 +40,7 @@ def run_attention(q, kv, kv_len, n_q, *, n_tail=0, tail_mask=None, window=-1, ca
     q_rows, H, _ = q.shape
     Hk = kv.k[layer].shape[1]
     G = H // Hk
-    out = torch.full_like(q, float("nan"))
+    out = torch.full((q_rows, H, 128), float("nan"), dtype=dtype, device=device)
     n_parts = n_splits if world_parts is None else world_parts
     part_o = torch.full((n_parts * Hk * q_rows * G * 128,), float("nan"), dtype=torch.float32, device=device)
     part_l = torch.full((n_parts * Hk * q_rows * G,), float("nan"), dtype=torch.float32, device=device)
@@ -50,7 +50,9 @@ def run_attention(q, kv, kv_len, n_q, *, n_tail=0, tail_mask=None, window=-1, ca
     if tail_mask is not None:
         bits = pack_bits(tail_mask).to(device)
     a = AttnDesc()
-    a.q, a.out = _ptr(q.contiguous()), _ptr(out)
+    strided = q.stride(0) != H * 128 and q.stride(1) == 128 and q.stride(2) == 1
+    a.q, a.out = _ptr(q if strided else q.contiguous()), _ptr(out)
+    a.q_stride = q.stride(0) if strided else 0
     a.k_pool, a.v_pool, a.page_table = _ptr(kv.k[layer]), _ptr(kv.v[layer]), _ptr(kv.page_table)
     a.kv_len_ptr, a.n_q_ptr, a.tail_mask = _ptr(kvl), _ptr(nq), _ptr(bits)
     a.part_o, a.part_lse = _ptr(part_o), _ptr(part_l)

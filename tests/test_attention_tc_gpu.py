@@ -84,3 +84,65 @@ def test_causal_rows_split_between_tc_and_remainder():
     mask = flash_ref.visible(n_q, n0, True)
     ref, _ = flash_ref.attend(q.float(), K.float(), V.float(), mask)
     torch.testing.assert_close(tc, ref, atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("splits", [1, 2, 12])
+def test_three_row_tiles_even_and_single_slot_plans(splits):
+    """296 packed rows = heavy/heavy/light CTA trios (even slot counts) or a heavy+light pair (one slot)."""
+    dtype = torch.bfloat16
+    n0 = 5000
+    q = gen((74, 8, 128), 1, dtype)
+    K = gen((n0 + 9, 2, 128), 2, dtype)
+    V = gen((n0 + 9, 2, 128), 3, dtype)
+    tc, mma = run_both(q, K, V, n0, 74, dtype, splits)
+    ref, _ = flash_ref.attend(q.float(), K[:n0].float(), V[:n0].float())
+    torch.testing.assert_close(tc, ref, atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("n_q", [1, 20, 40, 64, 65, 73])
+def test_runtime_rows_below_the_static_plan(n_q):
+    """The grid is planned from q_rows (74 -> three row tiles); the device-side row count may leave the light CTA,
+    or the second row tile, without a single live row (veri_rows = acc_num + S < q_v, engine.py)."""
+    from gpu_util import paged_from_dense, run_attention
+    dtype = torch.bfloat16
+    dev = torch.device("cuda:0")
+    n0 = 3000
+    q = gen((74, 8, 128), 1, dtype)
+    K = gen((n0, 2, 128), 2, dtype)
+    V = gen((n0, 2, 128), 3, dtype)
+    kv = paged_from_dense(K, V, dtype, dev)
+    out, _, _ = run_attention(q.to(dev), kv, n0, n_q, n_splits=6)
+    ref, _ = flash_ref.attend(q[:n_q].float(), K.float(), V.float())
+    torch.testing.assert_close(out[:n_q].float().cpu(), ref, atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("entry", ["ls_attn_partial", "ls_attn_partial_mma"])
+def test_q_read_in_place_from_a_fused_qkv_row(entry):
+    """q_stride: the q slice of a [rows][H*128 + 2*Hk*128] QKV GEMM output is consumed without a copy."""
+    from gpu_util import paged_from_dense, run_attention
+    dtype = torch.bfloat16
+    dev = torch.device("cuda:0")
+    n0, n_q, H, Hk = 2000, 74, 8, 2
+    qkv = gen((n_q, (H + 2 * Hk) * 128), 1, dtype).to(dev)
+    q = qkv[:, :H * 128].view(n_q, H, 128)
+    assert not q.is_contiguous()
+    K = gen((n0, Hk, 128), 2, dtype)
+    V = gen((n0, Hk, 128), 3, dtype)
+    kv = paged_from_dense(K, V, dtype, dev)
+    out, _, _ = run_attention(q, kv, n0, n_q, n_splits=4, entry=entry)
+    ref, _ = flash_ref.attend(q.float().cpu(), K.float(), V.float())
+    torch.testing.assert_close(out.float().cpu(), ref, atol=2e-2, rtol=2e-2)
+
+
+def test_more_slots_than_tiles_leaves_empty_ctas_harmless():
+    """Two row tiles and far more slots than key tiles: CTAs without any tile must publish empty partials
+    (zeros and -inf), never stale TMEM bits."""
+    dtype = torch.bfloat16
+    n0 = 700
+    q = gen((40, 8, 128), 1, dtype)
+    K = gen((n0 + 9, 2, 128), 2, dtype)
+    V = gen((n0 + 9, 2, 128), 3, dtype)
+    tc, mma = run_both(q, K, V, n0, 40, dtype, splits=16)
+    ref, _ = flash_ref.attend(q.float(), K[:n0].float(), V[:n0].float())
+    assert torch.isfinite(tc).all()
+    torch.testing.assert_close(tc, ref, atol=2e-2, rtol=2e-2)

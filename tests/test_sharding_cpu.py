@@ -77,3 +77,18 @@ def test_sharded_partials_exchange_and_merge_gloo(world):
         ret = mgr.dict()
         mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
         assert all(ret.get(r) for r in range(world))
+
+
+def test_split_plan_is_identical_on_every_rank():
+    """The partial-slot plan must not depend on the rank's own shard size (unequal shards once hung the exchange)."""
+    from longspec_b200.engine import Shard, split_plan
+    for world in (1, 2, 4, 8):
+        for P in (700, 3000, 16384, 131072):
+            total = P + 96 + 256 + 74 + 128
+            plan = split_plan(32, 8, 148, P, total, world, (74, 16, 1))
+            assert all(n >= 1 for n in plan) and plan[0] % 2 == 0       # three row tiles -> trios -> even slot count
+            sizes = [Shard.make(P, r, world) for r in range(world)]
+            assert sizes[-1].end == -1 and sizes[0].begin == 0
+    # world 2, 3000-token prompt: rank 0 holds 1536 tokens, rank 1 the rest + everything generated
+    a, b = Shard.make(3000, 0, 2), Shard.make(3000, 1, 2)
+    assert (a.begin, a.end, b.begin, b.end) == (0, 1536, 1536, -1)

@@ -22,7 +22,7 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_t, uint32_t b_lo, 
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n}" ::"r"(d), "r"(a_t), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ int RANDOM_DATA = 0;
-template <int MODE, int BN, int PV_TS, int WIDE = 0, int SPIN = 0, int ELECT = 0>
+template <int MODE, int BN, int PV_TS, int WIDE = 0, int SPIN = 0, int ELECT = 0, int ALT = 0>
 __global__ void k(int bursts, long long* out) {
     extern __shared__ uint8_t raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
@@ -68,8 +68,9 @@ __global__ void k(int bursts, long long* out) {
                     else mma_ss(tmem + 256 + (i % 2) * 128, p_lo + (kk & 3) * 2 + (kk >> 2) * 1024, bv_lo + (kk & 3) * 128 + (kk >> 2) * 2048, idv, kk > 0);
                 }
 #pragma unroll
+                const uint32_t a_alt = ALT ? a_lo + (i & 1) * 2048 : a_lo;   // ALT: Q tile 0 / Q tile 1 on alternate steps
                 for (int kk = 0; kk < 8; ++kk)                   // QK(t+2): K = 128 (head dim)
-                    mma_ss(sbuf, a_lo + (kk >> 2) * 1024 + (kk & 3) * 2, bk_lo + (kk >> 2) * (WIDE ? 1024 : BN * 8) + (kk & 3) * 2, idk, kk > 0);
+                    mma_ss(sbuf, a_alt + (kk >> 2) * 1024 + (kk & 3) * 2, bk_lo + (kk >> 2) * (WIDE ? 1024 : BN * 8) + (kk & 3) * 2, idk, kk > 0);
                 if (MODE == 1 || i == bursts - 1)
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
             }
@@ -89,15 +90,15 @@ __global__ void k(int bursts, long long* out) {
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 static int GRID = 1;
-template <int MODE, int BN, int PV_TS, int WIDE = 0, int SPIN = 0, int ELECT = 0>
+template <int MODE, int BN, int PV_TS, int WIDE = 0, int SPIN = 0, int ELECT = 0, int ALT = 0>
 void run(long long* d) {
-    cudaFuncSetAttribute(k<MODE, BN, PV_TS, WIDE, SPIN, ELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k<MODE, BN, PV_TS, WIDE, SPIN, ELECT, ALT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const int bursts = 4096;
-    k<MODE, BN, PV_TS, WIDE, SPIN, ELECT><<<GRID, SPIN ? 384 : 128, 200 * 1024>>>(bursts, d);
-    k<MODE, BN, PV_TS, WIDE, SPIN, ELECT><<<GRID, SPIN ? 384 : 128, 200 * 1024>>>(bursts, d);
+    k<MODE, BN, PV_TS, WIDE, SPIN, ELECT, ALT><<<GRID, SPIN ? 384 : 128, 200 * 1024>>>(bursts, d);
+    k<MODE, BN, PV_TS, WIDE, SPIN, ELECT, ALT><<<GRID, SPIN ? 384 : 128, 200 * 1024>>>(bursts, d);
     cudaDeviceSynchronize();
     long long h; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-    printf("%s%s%s BN=%3d PV=%s %-22s: %7.1f cycles per step (%d PV + 8 QK MMAs) = %.1f per 64 keys   %s\n", WIDE ? "16K-chunk-strides" : "compact", SPIN ? " +8 warps spinning on try_wait" : "", ELECT ? " +elect per burst" : "", BN, PV_TS ? "TS" : "SS",
+    printf("%s%s%s%s BN=%3d PV=%s %-22s: %7.1f cycles per step (%d PV + 8 QK MMAs) = %.1f per 64 keys   %s\n", WIDE ? "16K-chunk-strides" : "compact", SPIN ? " +8 warps spinning on try_wait" : "", ELECT ? " +elect per burst" : "", ALT ? " +alternating Q tile" : "", BN, PV_TS ? "TS" : "SS",
            MODE ? "wait after each burst" : "back to back", double(h) / bursts, BN / 16, double(h) / bursts * 64 / BN,
            cudaGetErrorString(cudaGetLastError()));
 }
@@ -111,6 +112,7 @@ int main(int argc, char** argv) {
     run<0, 64, 1, 1, 1, 0>(d); run<1, 64, 1, 1, 1, 0>(d);
     run<0, 64, 1, 1, 0, 1>(d); run<1, 64, 1, 1, 0, 1>(d);
     run<0, 64, 1, 1, 1, 1>(d); run<1, 64, 1, 1, 1, 1>(d);
+    run<0, 64, 1, 1, 0, 0, 1>(d); run<1, 64, 1, 1, 0, 0, 1>(d);
     run<0, 64, 0>(d); run<1, 64, 0>(d);
     run<0, 128, 1>(d); run<1, 128, 1>(d);
     run<0, 128, 0>(d); run<1, 128, 0>(d);
