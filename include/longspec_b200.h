@@ -91,7 +91,9 @@ typedef struct ls_attn_desc {
     int32_t window;             /* -1 = unbounded, else left window (512 for the draft) */
     int32_t causal;             /* 0/1 */
     int32_t dtype;              /* LS_F16 / LS_BF16 */
-    int32_t n_splits;           /* split-KV CTAs per kv head on this GPU (>= 1) */
+    int32_t n_splits;           /* split-KV partial slots per kv head this GPU writes (>= 1); the tcgen05 path runs
+                                   1 CTA per slot up to 256 packed rows and 1.5 CTAs per slot (heavy/heavy/light
+                                   trios, attn_tc.cu) for 257..384 packed rows */
     int32_t n_pages;            /* pages in k_pool / v_pool (extent of the TMA tensor maps) */
     int32_t part_offset;        /* first partial slot this launch writes (sequence-sharded multi-GPU) */
     int32_t n_parts_total;      /* partial slots the combine step reduces over */
@@ -107,8 +109,9 @@ typedef struct ls_attn_desc {
 int ls_attn_partial(const ls_attn_desc* d, void* stream);
 /* the general mma.sync data path behind ls_attn_partial (kept callable for cross-checks) */
 int ls_attn_partial_mma(const ls_attn_desc* d, void* stream);
-/* the tcgen05/TMA data path: unmasked full 64-key tiles of the prefix, n_splits_tc splits (window < 0,
- * <= 384 packed rows); ls_attn_partial pairs it with one mma.sync split for the masked remainder */
+/* the tcgen05/TMA data path alone: unmasked full 128-key tiles of the prefix into n_splits_tc slots (window < 0,
+ * <= 384 packed rows).  ls_attn_partial runs the same kernel with the masked remainder fused in as special tiles;
+ * LONGSPEC_ATTN=tc+mma pairs this entry with one mma.sync slot for the remainder instead (cross-check) */
 int ls_attn_partial_tc(const ls_attn_desc* d, int32_t n_splits_tc, void* stream);
 /* reduces n_parts_total partial slots and writes `out`; run after the partials of all ranks are
  * in the workspace (single GPU: right after ls_attn_partial) */
