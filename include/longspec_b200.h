@@ -116,6 +116,11 @@ int ls_attn_partial_tc(const ls_attn_desc* d, int32_t n_splits_tc, void* stream)
 /* reduces n_parts_total partial slots and writes `out`; run after the partials of all ranks are
  * in the workspace (single GPU: right after ls_attn_partial) */
 int ls_attn_combine(const ls_attn_desc* d, void* stream);
+/* multi-GPU: merges this launch's OWN slots [part_offset, part_offset + n_splits) into one normalised fp32
+ * partial dst_o [n_kv_heads][q_rows*group][128] + natural-log LSE dst_lse [n_kv_heads][q_rows*group] - the
+ * block a rank contributes to the exchange (1/n_splits of the raw slots); the final ls_attn_combine then runs
+ * over the gathered blocks with n_parts_total = world.  No reference counterpart (single GPU). */
+int ls_attn_reduce(const ls_attn_desc* d, float* dst_o, float* dst_lse, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * RoPE + KV append.  Replaces apply_rotary_pos_emb (llama.py:378, llama_glide.py:256,294) and

@@ -49,6 +49,7 @@ _SIGS = {
     "ls_attn_partial_mma": (i32, [C.POINTER(AttnDesc), vp]),
     "ls_attn_partial_tc": (i32, [C.POINTER(AttnDesc), i32, vp]),
     "ls_attn_combine": (i32, [C.POINTER(AttnDesc), vp]),
+    "ls_attn_reduce": (i32, [C.POINTER(AttnDesc), vp, vp, vp]),
     "ls_rope_append": (i32, [vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, i32, i32, i32, vp]),
     "ls_round_begin": (i32, [C.POINTER(TreeState), vp]),
     "ls_grow_workspace_bytes": (i64, [i32, i32]),

@@ -336,8 +336,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) attn_partial_kernel(const ls_a
 // One warp per (packed row, kv head): merge n_parts_total partials, write `out` in dtype.  The LSEs of up to 32
 // parts are held one per lane, weights are broadcast by shuffle and the 512-byte partial rows are fetched with
 // independent 16-byte loads (4 in flight per lane), so the merge is bandwidth- rather than latency-bound.
-template <typename T>
-__global__ void __launch_bounds__(256) attn_combine_kernel(const ls_attn_desc d) {
+// REDUCE = false: merge all n_parts_total slots and write `out` (dtype).  REDUCE = true (ls_attn_reduce): merge only
+// this launch's own slots [part_offset, part_offset + n_splits) into ONE normalised fp32 partial + LSE at
+// dst_o / dst_lse (slot layout [kv head][row][128]) - the block a rank contributes to the multi-GPU exchange.
+template <typename T, bool REDUCE>
+__global__ void __launch_bounds__(256) attn_combine_kernel(const ls_attn_desc d, float* __restrict__ dst_o, float* __restrict__ dst_lse) {
     const int G = d.n_heads / d.n_kv_heads;
     const int Rtot = d.q_rows * G;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -348,10 +351,11 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const ls_attn_desc d)
     const int n_q = min(*d.n_q_ptr, d.q_rows);
     T* out = reinterpret_cast<T*>(d.out) + (static_cast<size_t>(i) * d.n_heads + kvh * G + g) * kD + lane * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float lse_out = -INFINITY;
     if (i < n_q) {
         const size_t stride = static_cast<size_t>(d.n_kv_heads) * Rtot;        // between parts, in rows
-        const size_t row0 = static_cast<size_t>(kvh) * Rtot + r;
-        const int P = d.n_parts_total;
+        const size_t row0 = static_cast<size_t>(kvh) * Rtot + r + (REDUCE ? d.part_offset * stride : 0);
+        const int P = REDUCE ? d.n_splits : d.n_parts_total;
         float mx = -INFINITY;
         for (int p = lane; p < P; p += 32) mx = fmaxf(mx, d.part_lse[p * stride + row0]);
         mx = warp_max(mx);
@@ -375,7 +379,14 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const ls_attn_desc d)
             wsum = warp_sum(wsum);
             const float inv = 1.f / wsum;
             acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+            lse_out = mx + logf(wsum);
         }
+    }
+    if (REDUCE) {
+        const size_t row = static_cast<size_t>(kvh) * Rtot + r;
+        *reinterpret_cast<float4*>(dst_o + row * kD + lane * 4) = acc;
+        if (lane == 0) dst_lse[row] = lse_out;
+        return;
     }
     uint2 pk;
     pk.x = Num<T>::pack(acc.x, acc.y);
@@ -437,8 +448,21 @@ extern "C" int ls_attn_combine(const ls_attn_desc* d, void* stream) {
     const int blocks = (warps + 7) / 8;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (d->dtype == LS_F16)
-        attn_combine_kernel<__half><<<blocks, 256, 0, st>>>(*d);
+        attn_combine_kernel<__half, false><<<blocks, 256, 0, st>>>(*d, nullptr, nullptr);
     else
-        attn_combine_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(*d);
+        attn_combine_kernel<__nv_bfloat16, false><<<blocks, 256, 0, st>>>(*d, nullptr, nullptr);
     return check_launch("ls_attn_combine");
+}
+
+extern "C" int ls_attn_reduce(const ls_attn_desc* d, float* dst_o, float* dst_lse, void* stream) {
+    using namespace ls;
+    int rc = validate(d);
+    if (rc != LS_OK) return rc;
+    LS_REQUIRE(dst_o && dst_lse, "ls_attn_reduce: null destination");
+    const int G = d->n_heads / d->n_kv_heads;
+    const int warps = d->q_rows * G * d->n_kv_heads;
+    const int blocks = (warps + 7) / 8;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    attn_combine_kernel<__nv_bfloat16, true><<<blocks, 256, 0, st>>>(*d, dst_o, dst_lse);   // dtype-independent (fp32 in, fp32 out)
+    return check_launch("ls_attn_reduce");
 }

@@ -3,24 +3,30 @@
 // Work unit: one CTA = (kv head, a share of the 128-key tiles, up to TWO row tiles of 128 packed query rows),
 // a packed row being r = token * G + head-in-group, so a K/V tile serves the whole GQA group and candidate tree.
 //
-// TMEM (512 columns) holds two 128-column S/P buffers and two 128-column O accumulators - the FA4 shape: two
-// independent QK -> softmax -> PV chains are in flight and every MMA is N = 128 (tensor-rate, not shared-memory
-// bound).  A call with three row tiles (the Llama-3 verify shape: 74 tokens x GQA-4 = 296 rows) is cut into
-// "trios": two HEAVY CTAs (row tiles 0-1, alternate key tiles of the group's range) and one LIGHT CTA (row tile 2,
-// every key tile of the range).  All three do the same number of (row tile, key tile) steps, and the light CTA's
-// K/V loads hit L2 behind the heavy CTAs' loads, so HBM still sees every byte once.
+// TMEM (512 columns) = four 64-column S/P buffers + two 128-column O accumulators - the FA4 shape.  A STEP is
+// (key tile, 64-key half, row tile); step t lives in S/P buffer t & 3 and accumulates into O accumulator t & 1,
+// which softmax warpgroup t & 1 owns together with the (m, l) row state in REGISTERS.  Two row tiles: one
+// warpgroup + accumulator per row tile.  One row tile: the warpgroups take alternate key halves into two
+// accumulators and the epilogue merges the two partial states.  Four buffers = four QK -> softmax -> PV chains in
+// flight; the measured limiter is shared-memory operand bandwidth.
+// A call with three row tiles (the Llama-3 verify shape: 74 tokens x GQA-4 = 296 rows) is cut into "trios": two
+// HEAVY CTAs (row tiles 0-1, alternate key tiles of the group's range) and one LIGHT CTA (row tile 2, every key
+// tile of the range).  All three run the same number of steps, and the light CTA's K/V loads hit L2 behind the
+// heavy CTAs' loads, so HBM still sees every byte once (ncu: dram bytes = algorithmic bytes).
 //
 //   warp 0              TMA producer: 128-key K and V tiles (2 x [128 x 128 B] boxes each, SWIZZLE_128B) from the
 //                       paged pool into separate 2-stage K and V rings, completion on mbarriers
-//   warp 1              MMA issuer (converged warp, one elected lane): S = Q K^T (M128 N128 K16 x8, SS) into S/P
-//                       buffer t & 1; O_r += P V (M128 N128 K16 x8, TS: P read from TMEM, V MN-major in smem).
-//                       In-order schedule  QK(0) QK(1) | P(0): PV(0) QK(2) | P(1): PV(1) QK(3) | ...  - MMAs of one
-//                       thread execute in issue order, so QK(t+2) cannot overwrite the buffer PV(t) still reads.
+//   warp 1              MMA issuer (converged warp, one elected lane): S = Q K^T (M128 N64 K16 x8, SS) and
+//                       O += P V (M128 N128 K16 x4, TS: P read from TMEM, V MN-major in smem), issued in PAIRS of
+//                       steps:  QK(pair 0) QK(pair 1) | P(0): PV(0) QK(2) | P(1): PV(1) QK(3) | ...
+//                       MMAs of one thread execute in issue order, so QK(pair p+2) cannot overwrite the buffers
+//                       PV(pair p) still reads: no "buffer free" barriers.  tcgen05.mma issue is throttled to the
+//                       pipe's execution rate, so the issuer does one wait and one commit per 24 MMAs.
 //   warp 2              TMEM allocation
-//   warps 4-7 / 8-11    two softmax warpgroups, alternating steps (with two row tiles: one warpgroup per row tile).
-//                       One row per thread, the 128-key tile in two 64-key halves: tcgen05.ld, online softmax in the
-//                       log2 domain with lazy rescaling (O in TMEM is only rescaled when a row maximum grows by more
-//                       than 2^8), P rounded to dtype and tcgen05.st IN PLACE over the S columns it came from.
+//   warps 4-7 / 8-11    two softmax warpgroups, one step of every pair each.  One row per thread: tcgen05.ld the
+//                       64-key S tile, online softmax in the log2 domain with lazy rescaling (O in TMEM is only
+//                       rescaled when a row maximum grows by more than 2^8), P rounded to dtype and tcgen05.st IN
+//                       PLACE over the first 32 columns of the S buffer it came from (S and P alias).
 // The masked remainder of the call (last partial prefix tile, causal rows, the tree-masked tail = this round's
 // tokens) is appended to the tile sequence as "special tiles" whose softmax applies a per-row bit mask, so one
 // launch covers the whole attention call.  The epilogue writes normalised partial O (fp32) and the natural-log
@@ -59,7 +65,6 @@ constexpr int OFF_SPECIAL = OFF_BAR + BAR_BYTES;
 constexpr int SMEM_BYTES = OFF_SPECIAL + SPECIAL_BYTES + 1024;   // + worst-case alignment of the dynamic base
 
 constexpr uint32_t TMEM_COLS = 512;
-constexpr int NBUF = 4;                            // S/P buffers = QK -> softmax -> PV chains in flight
 constexpr uint32_t COL_SP = 0;                     // four buffers of 64 columns: a 128 x 64 fp32 score tile, overwritten
                                                    // in place by its 128 x 64 bf16/fp16 probability tile (32 columns)
 constexpr uint32_t COL_O = 256;                    // 2 x 128

@@ -274,11 +274,18 @@ class Engine:
         self.n_split_verify, self.n_split_cross, self.n_split_one = plan
         self.n_split_self = 4
         world = sh.world
-        max_parts = max(self.n_split_verify, self.n_split_cross, self.n_split_one) * world
+        max_parts = max(self.n_split_verify, self.n_split_cross, self.n_split_one)
         max_parts = max(max_parts, self.n_split_self)
         rows_max = self.q_v * G
         self.part_o = torch.empty(max_parts * d.kv_heads * rows_max * 128, dtype=torch.float32, device=dev)
         self.part_lse = torch.empty(max_parts * d.kv_heads * rows_max, dtype=torch.float32, device=dev)
+        # multi-GPU exchange blocks: ONE locally reduced (O, lse) partial per rank and attention call
+        self.xchg_o = self.xchg_lse = None
+        if world > 1:
+            self.xchg_o = torch.empty(world * d.kv_heads * rows_max * 128, dtype=torch.float32, device=dev)
+            self.xchg_lse = torch.empty(world * d.kv_heads * rows_max, dtype=torch.float32, device=dev)
+            self.send_o = torch.empty(d.kv_heads * rows_max * 128, dtype=torch.float32, device=dev)
+            self.send_lse = torch.empty(d.kv_heads * rows_max, dtype=torch.float32, device=dev)
         self.grow_ws = torch.empty(int(_lib.load().ls_grow_workspace_bytes(32, d.vocab)), dtype=torch.uint8, device=dev)
         self.descs = []                                # keep ctypes structs alive
 
@@ -297,7 +304,7 @@ class Engine:
         a.kv_len_bias, a.q_rows, a.n_heads, a.n_kv_heads = kv_len_bias, q_rows, d.heads, d.kv_heads
         a.n_tail, a.window, a.causal, a.dtype = n_tail, window, causal, self.code
         a.n_splits, a.n_pages = n_splits, kvp.n_pages
-        a.part_offset, a.n_parts_total = sh.rank * n_splits, sh.world * n_splits
+        a.part_offset, a.n_parts_total = 0, n_splits            # local slots; ranks meet in the exchange blocks (_attn)
         a.kv_shard_begin, a.kv_shard_end, a.tail_owner = sh.begin, sh.end, int(sh.owner)
         a.scale = self.scale
         a.q_stride = q.stride(0)             # the q slice of a fused QKV output is read in place
@@ -309,18 +316,30 @@ class Engine:
         self.descs.append(a)
         _lib.call("ls_attn_partial", C.byref(a), _stream())
         if sharded and self.shard.world > 1:
-            self._exchange_partials(a, q_rows)
+            a = self._exchange_partials(a, q_rows)
         _lib.call("ls_attn_combine", C.byref(a), _stream())
         self.launches += 2
 
     def _exchange_partials(self, a, q_rows):
-        """Sequence-sharded prefix: one NCCL all-gather of the per-rank (O, lse) partial slots per attention
-        call (SURVEY.md section 8(e) option A - deterministic merge order on every rank)."""
+        """Sequence-sharded prefix (option A with a deterministic merge order): every rank
+        reduces its own split-KV slots to ONE normalised (O, lse) block (ls_attn_reduce), one NCCL all-gather makes
+        the `world` blocks visible everywhere, and the returned descriptor lets ls_attn_combine merge them - the
+        same data in the same order on every rank, hence bit-identical accept decisions.  Bytes on the wire per call
+        and rank: Hk * rows * G * 129 * 4 (1.2 MB at the Llama-3 verify shape)."""
         from .parallel import exchange_partials
-        d = self.dims
+        d, sh = self.dims, self.shard
         G = d.heads // d.kv_heads
-        n_l = a.n_splits * d.kv_heads * q_rows * G
-        exchange_partials(self.part_o, self.part_lse, n_l * 128, n_l, self.shard.rank, self.shard.world, self.group)
+        n_l = d.kv_heads * q_rows * G
+        n_o = n_l * 128
+        _lib.call("ls_attn_reduce", C.byref(a), _ptr(self.send_o), _ptr(self.send_lse), _stream())
+        self.launches += 1
+        exchange_partials(self.xchg_o, self.xchg_lse, n_o, n_l, sh.rank, sh.world, self.group, mine=(self.send_o, self.send_lse))
+        b = AttnDesc()
+        C.memmove(C.byref(b), C.byref(a), C.sizeof(AttnDesc))
+        b.part_o, b.part_lse = _ptr(self.xchg_o), _ptr(self.xchg_lse)
+        b.part_offset, b.n_splits, b.n_parts_total = 0, sh.world, sh.world
+        self.descs.append(b)
+        return b
 
     def _rope_append(self, q, k, v, q_stride, kv_stride, positions, pools, layer, base_len_ptr, base_bias, slot_offset,
                      n_rows_ptr, rows, append=True):

@@ -15,17 +15,21 @@ import torch.distributed as dist
 
 
 def exchange_partials(part_o: torch.Tensor, part_lse: torch.Tensor, n_o: int, n_l: int, rank: int, world: int,
-                      group=None) -> None:
+                      group=None, mine=None) -> None:
     """All-gather the partial slots in place.
 
-    part_o / part_lse are the flat workspaces of ls_attn_desc; rank r has written its slots at
-    [r * n_o, (r + 1) * n_o) and [r * n_l, (r + 1) * n_l) (part_offset = r * n_splits).  After the
-    call every rank holds all world * n_splits slots in rank order - the layout ls_attn_combine reads.
+    part_o / part_lse are flat workspaces in the slot layout of ls_attn_desc; rank r contributes a block of
+    n_o / n_l floats (the engine: ONE locally reduced partial per rank, ls_attn_reduce) - either already in
+    place at [r * n_o, (r + 1) * n_o) / [r * n_l, (r + 1) * n_l), or in the separate send buffers `mine`.
+    After the call every rank holds all `world` blocks in rank order - the layout ls_attn_combine reads.
     """
     o_all = part_o[:n_o * world]
     l_all = part_lse[:n_l * world]
-    o_mine = o_all[rank * n_o:(rank + 1) * n_o].clone()
-    l_mine = l_all[rank * n_l:(rank + 1) * n_l].clone()
+    if mine is not None:            # this rank's block already sits in separate send buffers: no staging copy
+        o_mine, l_mine = mine[0][:n_o], mine[1][:n_l]
+    else:
+        o_mine = o_all[rank * n_o:(rank + 1) * n_o].clone()
+        l_mine = l_all[rank * n_l:(rank + 1) * n_l].clone()
     if part_o.is_cuda:
         # one NCCL group launch for both tensors (the exchange is latency-, not bandwidth-bound)
         with dist._coalescing_manager(group=group, device=part_o.device, async_ops=False):

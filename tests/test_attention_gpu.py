@@ -192,6 +192,59 @@ def test_sequence_sharded_partials_combine_to_the_same_result():
     torch.testing.assert_close(res[:n_valid].float(), full[:n_valid].float(), atol=1e-2, rtol=1e-2)
 
 
+def test_sharded_two_level_merge_matches_unsharded():
+    """The engine's multi-GPU path on one GPU: each 'rank' reduces its own slots to one (O, lse) block with
+    ls_attn_reduce, the blocks are laid out like the all-gather leaves them, and ls_attn_combine merges `world`
+    blocks (engine._exchange_partials).  Must equal the unsharded result; the wide verify shape (three row tiles)."""
+    import ctypes as C
+    from longspec_b200 import _lib
+    from longspec_b200._lib import AttnDesc
+    from longspec_b200.engine import _ptr, _stream, _code
+    from gpu_util import paged_from_dense, run_attention
+    dev = torch.device("cuda:0")
+    dtype = torch.bfloat16
+    H, Hk, n0 = 8, 2, 2500
+    tm, offs = random_tree_mask([4, 16, 16, 16, 16], 3)
+    vm = verify_mask(tm, 3, 5)
+    qv = vm.shape[0]
+    n_valid = 3 + tm.shape[0] - 1
+    G = H // Hk
+    q = gen((qv, H, 128), 1, dtype).to(dev)
+    Kc = gen((n0 + qv + 9, Hk, 128), 4, dtype)
+    Vc = gen((n0 + qv + 9, Hk, 128), 5, dtype)
+    kv_full = paged_from_dense(Kc, Vc, dtype, dev)
+    full, _, _ = run_attention(q, kv_full, n0, n_valid, n_tail=qv, tail_mask=vm, n_splits=4)
+    bounds = [(0, 1024), (1024, 2048), (2048, -1)]
+    n_splits, world = 2, 3
+    n_l = Hk * qv * G
+    xo = torch.full((world * n_l * 128,), float("nan"), dtype=torch.float32, device=dev)
+    xl = torch.full((world * n_l,), float("nan"), dtype=torch.float32, device=dev)
+    kvl = torch.tensor([n0], dtype=torch.int32, device=dev)
+    nq = torch.tensor([n_valid], dtype=torch.int32, device=dev)
+
+    def desc(po, pl, out, parts, splits):
+        a = AttnDesc()
+        a.q, a.out, a.k_pool, a.v_pool, a.page_table = _ptr(q), _ptr(out), _ptr(kv_full.k[0]), _ptr(kv_full.v[0]), _ptr(kv_full.page_table)
+        a.kv_len_ptr, a.n_q_ptr, a.part_o, a.part_lse = _ptr(kvl), _ptr(nq), _ptr(po), _ptr(pl)
+        a.q_rows, a.n_heads, a.n_kv_heads, a.dtype = qv, H, Hk, _code(dtype)
+        a.n_splits, a.part_offset, a.n_parts_total = splits, 0, parts
+        a.kv_shard_begin, a.kv_shard_end, a.tail_owner, a.window = 0, -1, 1, -1
+        return a
+    scratch = torch.empty_like(q)
+    for r, (b, e) in enumerate(bounds):
+        hi = Kc.shape[0] if e < 0 else e
+        kv = paged_from_dense(Kc[b:hi], Vc[b:hi], dtype, dev)
+        _, po, pl = run_attention(q, kv, n0, n_valid, n_tail=qv, tail_mask=vm, n_splits=n_splits, shard=(b, e, int(e < 0)))
+        a = desc(po, pl, scratch, n_splits, n_splits)
+        _lib.call("ls_attn_reduce", C.byref(a), _ptr(xo[r * n_l * 128:]), _ptr(xl[r * n_l:]), _stream())
+    res = torch.empty_like(q)
+    a = desc(xo, xl, res, world, world)
+    _lib.call("ls_attn_combine", C.byref(a), _stream())
+    torch.cuda.synchronize()
+    assert torch.isfinite(xl.view(world, Hk, qv * G)[:, :, :n_valid * G]).all()
+    torch.testing.assert_close(res[:n_valid].float(), full[:n_valid].float(), atol=1e-2, rtol=1e-2)
+
+
 def test_full_size_prefix_uniform_attention_property():
     """Full-size property check (N = 131072, Llama-3-8B GQA-4 verify shape, BASELINE configs[2]): with
     K = 0 every key gets equal weight, so the output must equal the mean of the visible V rows -
