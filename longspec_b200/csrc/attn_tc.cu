@@ -380,22 +380,24 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         const int ppt = NR;                           // pairs per key tile
         int pq = 0, iq = 0, sq = 0, phq = 0;          // next QK pair: index inside its key tile, K stage, K_FULL parity
         int ip = 0, sp = 0, php = 0;                  // next PV pair: index inside its key tile, V stage, V_FULL parity
-        // QK MMAs of pair pq (elected lane only) / bookkeeping of the QK cursor (whole warp)
-        auto qk_pair_mmas = [&]() {
+        auto issue_qk_pair = [&]() {
+            if (iq == 0 && !LS_DBG(16)) mbar_wait(bar(B_K_FULL + sq), phq);
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) {
-                const int h = NR == 2 ? iq : s2, r = NR == 2 ? s2 : 0;
-                const uint32_t a0 = q_lo + r * (32768 >> 4), b0 = k_lo + sq * (TILE_BYTES >> 4) + h * (8192 >> 4);
-                const uint32_t dst = tmem + COL_SP + ((2 * pq + s2) & 3) * 64;
-                if (!LS_DBG(2))
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const int h = NR == 2 ? iq : s2, r = NR == 2 ? s2 : 0;
+                    const uint32_t a0 = q_lo + r * (32768 >> 4), b0 = k_lo + sq * (TILE_BYTES >> 4) + h * (8192 >> 4);
+                    const uint32_t dst = tmem + COL_SP + ((2 * pq + s2) & 3) * 64;
+                    if (!LS_DBG(2))
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk)
-                    tc_mma2(dst, a0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2, b0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2,
-                            IDESC_QK, kk > 0 ? 1u : 0u);
+                    for (int kk = 0; kk < 8; ++kk)
+                        tc_mma2(dst, a0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2, b0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2,
+                                IDESC_QK, kk > 0 ? 1u : 0u);
+                }
+                if (iq == ppt - 1) tc_commit(bar(B_K_EMPTY + sq));
             }
-            if (iq == ppt - 1) tc_commit(bar(B_K_EMPTY + sq));
-        };
-        auto qk_advance = [&]() {
+            __syncwarp();
             ++pq;
             if (++iq == ppt) {
                 iq = 0;
@@ -403,20 +405,12 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
             }
         };
         for (int i = 0; i < 2 && i < n_pairs; ++i) {
-            if (iq == 0 && !LS_DBG(16)) mbar_wait(bar(B_K_FULL + sq), phq);
-            tc_fence_after();
-            if (elect_one()) {
-                qk_pair_mmas();
-                tc_commit(bar(B_S_FULL + i));
-            }
+            issue_qk_pair();
+            if (elect_one()) tc_commit(bar(B_S_FULL + i));
             __syncwarp();
-            qk_advance();
         }
         for (int p = 0; p < n_pairs; ++p) {
-            // all waits first, then ONE elected block issues PV(pair p), QK(pair p+2) and the commits back to back
-            const bool do_qk = pq < n_pairs;
             if (ip == 0 && !LS_DBG(16)) mbar_wait(bar(B_V_FULL + sp), php);
-            if (do_qk && iq == 0 && !LS_DBG(16)) mbar_wait(bar(B_K_FULL + sq), phq);
             if (!LS_DBG(8)) mbar_wait(bar(B_P_FULL + (p & 1)), (p >> 1) & 1);
             tc_fence_after();
             if (lane == 0) LS_TRACE(0, p);
@@ -432,15 +426,15 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                         tc_mma_ts(dst, a0 + kk * 8, b0 + kk * (2048 >> 4), IDESC_PV, (p > 0 || kk > 0) ? 1u : 0u);
                 }
                 if (ip == ppt - 1) tc_commit(bar(B_V_EMPTY + sp));
-                if (do_qk) qk_pair_mmas();
-                tc_commit(bar(B_S_FULL + (p & 1)));      // S of pair p+2 is ready / PV of pair p is complete
             }
             __syncwarp();
             if (++ip == ppt) {
                 ip = 0;
                 if (++sp == STAGES) { sp = 0; php ^= 1; }
             }
-            if (do_qk) qk_advance();
+            if (pq < n_pairs) issue_qk_pair();
+            if (elect_one()) tc_commit(bar(B_S_FULL + (p & 1)));   // S of pair p+2 is ready / PV of pair p is complete
+            __syncwarp();
             if (lane == 0) LS_TRACE(1, p);
         }
         if (n_steps > 0 && elect_one()) tc_commit(bar(B_ALL_DONE));   // every MMA of this CTA has completed once this fires
