@@ -145,7 +145,10 @@ class CpuSample:
         return dt
 
     def calibrate(self):
-        t1, t2 = self.round(1), self.round(2)
+        # best of two per depth: the first pass through a freshly allocated model pays page faults / thread start-up,
+        # which would otherwise swamp the difference between the 1- and the 2-layer round
+        t1 = min(self.round(1), self.round(1))
+        t2 = min(self.round(2), self.round(2))
         self.per_layer = max(t2 - t1, 0.0)
         self.models.pop(2, None)
         return t1, t2
@@ -162,7 +165,7 @@ def cpu_baseline(tau, threads):
             "seconds_per_round": total,
             "sample": (f"oracle (CPU port of the reference's PyTorch-eager tree path, fp32, {threads} threads): one decode "
                        f"round at {MODEL} widths, {PROMPT}-token context, tree {TREE}, target truncated to 1 and 2 layers "
-                       f"({t1:.2f} s, {t2:.2f} s) and extrapolated linearly to full depth; random KV stands in "
+                       f"(best of two each: {t1:.2f} s, {t2:.2f} s) and extrapolated linearly to full depth; random KV stands in "
                        f"for the prefill; tokens/round = tau of the GPU run ({tau:.2f})")}
 
 

@@ -98,3 +98,30 @@ def test_shard_partition_covers_the_prompt():
             for a, b in zip(sh[:-1], sh[1:]):
                 assert a.end == b.begin and a.begin % 128 == 0 and not a.owner
             assert sh[-1].begin <= P
+
+
+def test_checkpoint_directories_load_with_the_reference_key_names(tmp_path):
+    """HF-style safetensors directories (target: `model.*` / `lm_head.*`; draft: LlamaGlideDecoderLayer keys without a
+    prefix, llama_glide.py:480) are read shard by shard; the draft's keys get the `glide.` prefix Weights expects."""
+    from safetensors.torch import save_file
+    from longspec_b200.llama_glide import _load_dir
+    from longspec_b200.synthetic import PRESETS, synthetic_state_dict
+    dims = PRESETS["tiny-gqa"]
+    sd = synthetic_state_dict(dims, seed=5)
+    target = {k: v.contiguous() for k, v in sd.items() if not k.startswith("glide.")}
+    draft = {k[len("glide."):]: v.contiguous() for k, v in sd.items() if k.startswith("glide.")}
+    tdir, gdir = tmp_path / "target", tmp_path / "glide"
+    tdir.mkdir()
+    gdir.mkdir()
+    keys = sorted(target)
+    half = len(keys) // 2
+    save_file({k: target[k] for k in keys[:half]}, str(tdir / "model-00001-of-00002.safetensors"))
+    save_file({k: target[k] for k in keys[half:]}, str(tdir / "model-00002-of-00002.safetensors"))
+    save_file(draft, str(gdir / "model.safetensors"))
+    got = _load_dir(str(tdir))
+    got.update(_load_dir(str(gdir), prefix="glide."))
+    assert sorted(got) == sorted(sd)
+    for k in sd:
+        assert torch.equal(got[k], sd[k]), k
+    with pytest.raises(FileNotFoundError):
+        _load_dir(str(tmp_path / "missing"))
