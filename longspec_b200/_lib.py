@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblongspec_b200.so")
+# LONGSPEC_LIB points the binding at an alternative build of the SAME ABI (tools/experimental/build_n128.sh, trace builds)
+LIB_PATH = os.environ.get("LONGSPEC_LIB") or os.path.join(HERE, "liblongspec_b200.so")
 
 LS_PAGE = 128
 LS_HEAD_DIM = 128

@@ -3,12 +3,13 @@
 // Work unit: one CTA = (kv head, a share of the 128-key tiles, up to TWO row tiles of 128 packed query rows),
 // a packed row being r = token * G + head-in-group, so a K/V tile serves the whole GQA group and candidate tree.
 //
-// TMEM (512 columns) = four 64-column S/P buffers + two 128-column O accumulators - the FA4 shape.  A STEP is
-// (key tile, 64-key half, row tile); step t lives in S/P buffer t & 3 and accumulates into O accumulator t & 1,
-// which softmax warpgroup t & 1 owns together with the (m, l) row state in REGISTERS.  Two row tiles: one
-// warpgroup + accumulator per row tile.  One row tile: the warpgroups take alternate key halves into two
-// accumulators and the epilogue merges the two partial states.  Four buffers = four QK -> softmax -> PV chains in
-// flight; the measured limiter is shared-memory operand bandwidth.
+// EXPERIMENTAL VARIANT (tools/experimental, not part of the default build; round-2 candidate, UNTESTED on hardware):
+// TMEM (512 columns) = two 128-column pair buffers + ONE 128-column O accumulator per row tile.  A PAIR is (key tile,
+// row tile): one QK^T with N = 128 keys (tensor-rate instead of the shared-memory-bound N = 64: 8 KB of operands per
+// MMA for twice the work of 6 KB), the two softmax warpgroups turn the two 64-key halves into P in place, one PV with
+// K = 128 keys.  Both warpgroups feed the same accumulator, so the two threads of a row share the reference maximum;
+// a bar.red.or per lane quarter decides whether any row has to move it (lazy rescale), see the softmax section.
+// Per (row tile, 128 keys) the CTA moves 128 KB through shared memory instead of 160 KB and issues 16 MMAs instead of 24.
 // A call with three row tiles (the Llama-3 verify shape: 74 tokens x GQA-4 = 296 rows) is cut into "trios": two
 // HEAVY CTAs (row tiles 0-1, alternate key tiles of the group's range) and one LIGHT CTA (row tile 2, every key
 // tile of the range).  All three run the same number of steps, and the light CTA's K/V loads hit L2 behind the
@@ -42,7 +43,7 @@
 #include <type_traits>
 #include <unordered_map>
 
-#include "common.cuh"
+#include "../../longspec_b200/csrc/common.cuh"
 
 namespace ls {
 namespace tc {
@@ -54,7 +55,7 @@ constexpr int STAGES = 2;                          // K ring and V ring depth
 constexpr int THREADS = 384;
 constexpr int TILE_BYTES = 32768;                  // one K or V tile: [2 x 64-element chunks][128 keys][128 B]
 constexpr int Q_BYTES = NRL_MAX * 32768;           // [row tile][2 k-chunks][128 rows][128 B]
-constexpr int STATE_BYTES = 2 * 2 * 128 * 4;       // epilogue exchange of (m_ref, l) between the warpgroups
+constexpr int STATE_BYTES = 2 * 2 * 128 * 4;       // exchange scratch between the warpgroups (maxima; row sums)
 constexpr int BAR_BYTES = 256;
 constexpr int SPECIAL_BYTES = 256;                 // special-tile table (12 x 16 B)
 constexpr int OFF_K = Q_BYTES;
@@ -282,16 +283,10 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
     const int tile_lo = min(share0 * per, all_tiles) + first;
     const int tile_hi = min((share0 + nshare) * per, all_tiles);
     const int n_tiles = (NR > 0 && tile_hi > tile_lo) ? (tile_hi - tile_lo + stride - 1) / stride : 0;
-    // A step = (key tile j, 64-key half h, row tile r), in that nesting; step t runs on S/P buffer t & 3 and its PV
-    // accumulates into O accumulator t & 1, which softmax warpgroup t & 1 owns.  With two row tiles that is "one
-    // warpgroup and one accumulator per row tile"; with one row tile the two warpgroups take alternate key halves
-    // into two accumulators with private (m, l) row states, merged in the epilogue.
-    const int spt = 2 * NR;                                          // steps per key tile
-    const int n_steps = n_tiles * spt;
+    // A pair = (key tile j, row tile r), r fastest; pair p runs in pair buffer p & 1 and accumulates into O_r.
+    const int n_steps = n_tiles * NR;                                // pairs of this CTA (name kept for the shared set-up code)
     auto tile_index = [&](int j) { return tile_lo + j * stride; };   // position in the call's tile sequence
 
-    float* st_m = reinterpret_cast<float*>(smem + OFF_STATE);        // epilogue exchange only (one row tile)
-    float* st_l = st_m + 2 * 128;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + B_COUNT * 8);
     const uint32_t bar0 = sbase + OFF_BAR;
     auto bar = [&](int i) { return bar0 + i * 8; };
@@ -334,7 +329,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
     const uint32_t tmem = *tmem_slot;
 
     constexpr int FMT = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
-    constexpr uint32_t IDESC_QK = make_idesc(128, 64, FMT, 0, 0);
+    constexpr uint32_t IDESC_QK = make_idesc(128, 128, FMT, 0, 0);
     constexpr uint32_t IDESC_PV = make_idesc(128, 128, FMT, 0, 1);
 
     if (warp == 0) {
@@ -365,289 +360,257 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        // The whole warp runs this loop converged (all values warp-uniform); one elected lane issues.
-        // Steps are issued in PAIRS (pair p = steps 2p, 2p+1 = one step of each softmax warpgroup); pair p lives in
-        // S/P buffers {0,1} (p even) or {2,3} (p odd).  In-order schedule:
-        //   QK(pair 0) QK(pair 1) | P(pair 0) ready: PV(pair 0) QK(pair 2) | P(pair 1) ready: PV(pair 1) QK(pair 3) | ...
-        // MMAs of one thread execute in issue order, so QK(pair p+2) cannot overwrite the buffers PV(pair p) still
-        // reads P from.  One commit per iteration: S_FULL of pair p+2, which also certifies PV(pair p) complete.
-        // (tcgen05.mma issue is throttled to the pipe's execution rate, so every instruction the issuing thread spends
-        // on barriers is tensor-pipe idle time - hence pairs: one wait and one commit per 24 MMAs.)
+        // PAIR p = (key tile j, row tile r): ONE QK^T of N = 128 keys into the 128-column pair buffer p & 1, whose two
+        // 64-key halves the two softmax warpgroups turn into P in place, then ONE PV (K = 128 keys) into the row tile's
+        // single accumulator.  In-order schedule:  QK(0) QK(1) | P(0): PV(0) QK(2) | P(1): PV(1) QK(3) | ...
         const uint32_t q_lo = (sbase >> 4) | LBO_K;
         const uint32_t k_lo = ((sbase + OFF_K) >> 4) | LBO_K;
         const uint32_t v_lo = ((sbase + OFF_V) >> 4) | LBO_V;
-        const int n_pairs = n_steps >> 1;
-        const int ppt = NR;                           // pairs per key tile
-        int pq = 0, iq = 0, sq = 0, phq = 0;          // next QK pair: index inside its key tile, K stage, K_FULL parity
-        int ip = 0, sp = 0, php = 0;                  // next PV pair: index inside its key tile, V stage, V_FULL parity
-        auto issue_qk_pair = [&]() {
-            if (iq == 0 && !LS_DBG(16)) mbar_wait(bar(B_K_FULL + sq), phq);
+        const int n_pairs = n_tiles * NR;
+        int pq = 0, rq = 0, sq = 0, phq = 0;          // next QK pair: row tile, K stage, K_FULL parity
+        int rp = 0, sp = 0, php = 0;                  // next PV pair: row tile, V stage, V_FULL parity
+        auto issue_qk = [&]() {
+            if (rq == 0) mbar_wait(bar(B_K_FULL + sq), phq);
             tc_fence_after();
             if (elect_one()) {
+                const uint32_t a0 = q_lo + rq * (32768 >> 4), b0 = k_lo + sq * (TILE_BYTES >> 4);
+                const uint32_t dst = tmem + COL_SP + (pq & 1) * 128;
 #pragma unroll
-                for (int s2 = 0; s2 < 2; ++s2) {
-                    const int h = NR == 2 ? iq : s2, r = NR == 2 ? s2 : 0;
-                    const uint32_t a0 = q_lo + r * (32768 >> 4), b0 = k_lo + sq * (TILE_BYTES >> 4) + h * (8192 >> 4);
-                    const uint32_t dst = tmem + COL_SP + ((2 * pq + s2) & 3) * 64;
-                    if (!LS_DBG(2))
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)
-                        tc_mma2(dst, a0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2, b0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2,
-                                IDESC_QK, kk > 0 ? 1u : 0u);
-                }
-                if (iq == ppt - 1) tc_commit(bar(B_K_EMPTY + sq));
+                for (int kk = 0; kk < 8; ++kk)
+                    tc_mma2(dst, a0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2, b0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2,
+                            IDESC_QK, kk > 0 ? 1u : 0u);
+                if (rq == NR - 1) tc_commit(bar(B_K_EMPTY + sq));
             }
             __syncwarp();
             ++pq;
-            if (++iq == ppt) {
-                iq = 0;
+            if (++rq == NR) {
+                rq = 0;
                 if (++sq == STAGES) { sq = 0; phq ^= 1; }
             }
         };
         for (int i = 0; i < 2 && i < n_pairs; ++i) {
-            issue_qk_pair();
+            issue_qk();
             if (elect_one()) tc_commit(bar(B_S_FULL + i));
             __syncwarp();
         }
         for (int p = 0; p < n_pairs; ++p) {
-            if (ip == 0 && !LS_DBG(16)) mbar_wait(bar(B_V_FULL + sp), php);
-            if (!LS_DBG(8)) mbar_wait(bar(B_P_FULL + (p & 1)), (p >> 1) & 1);
+            if (rp == 0) mbar_wait(bar(B_V_FULL + sp), php);
+            mbar_wait(bar(B_P_FULL + (p & 1)), (p >> 1) & 1);
             tc_fence_after();
             if (lane == 0) LS_TRACE(0, p);
             if (elect_one()) {
+                const uint32_t pbuf = tmem + COL_SP + (p & 1) * 128, b0 = v_lo + sp * (TILE_BYTES >> 4);
+                const uint32_t dst = tmem + COL_O + rp * 128;
 #pragma unroll
-                for (int s2 = 0; s2 < 2; ++s2) {
-                    const int h = NR == 2 ? ip : s2;
-                    const uint32_t a0 = tmem + COL_SP + ((2 * p + s2) & 3) * 64, b0 = v_lo + sp * (TILE_BYTES >> 4) + h * (8192 >> 4);
-                    const uint32_t dst = tmem + COL_O + s2 * 128;
-                    if (!LS_DBG(1))
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)      // 16 keys = 8 packed TMEM columns per K step
-                        tc_mma_ts(dst, a0 + kk * 8, b0 + kk * (2048 >> 4), IDESC_PV, (p > 0 || kk > 0) ? 1u : 0u);
-                }
-                if (ip == ppt - 1) tc_commit(bar(B_V_EMPTY + sp));
+                for (int kk = 0; kk < 8; ++kk)      // P of keys 0-63 sits in columns 0-31, of keys 64-127 in columns 64-95
+                    tc_mma_ts(dst, pbuf + (kk >> 2) * 64 + (kk & 3) * 8, b0 + kk * (2048 >> 4), IDESC_PV,
+                              (p >= NR || kk > 0) ? 1u : 0u);
+                if (rp == NR - 1) tc_commit(bar(B_V_EMPTY + sp));
             }
             __syncwarp();
-            if (++ip == ppt) {
-                ip = 0;
+            if (++rp == NR) {
+                rp = 0;
                 if (++sp == STAGES) { sp = 0; php ^= 1; }
             }
-            if (pq < n_pairs) issue_qk_pair();
+            if (pq < n_pairs) issue_qk();
             if (elect_one()) tc_commit(bar(B_S_FULL + (p & 1)));   // S of pair p+2 is ready / PV of pair p is complete
             __syncwarp();
             if (lane == 0) LS_TRACE(1, p);
         }
-        if (n_steps > 0 && elect_one()) tc_commit(bar(B_ALL_DONE));   // every MMA of this CTA has completed once this fires
+        if (n_pairs > 0 && elect_one()) tc_commit(bar(B_ALL_DONE));   // every MMA of this CTA has completed once this fires
         __syncwarp();
     } else if (warp >= 4) {
         // ================= softmax warpgroups =================
-        const int wg = (warp - 4) >> 2;                              // = step parity = O accumulator
+        // Warpgroup w owns the 64-key half w of EVERY pair; the two threads (w = 0, 1) of a row share the row's
+        // reference maximum m_ref - identical in both by construction - and keep private partial sums l.  The lazy
+        // rescale needs both halves' maxima: one bar.red.or over the 64 threads of the two warps that share a TMEM lane
+        // quarter tells both warps whether ANY of their rows has to move its reference; only then do they exchange
+        // maxima through shared memory and rescale the accumulator (each thread 64 of its row's 128 columns).
+        const int wg = (warp - 4) >> 2;                              // = 64-key half of every pair
         const int quad = warp & 3;                                   // TMEM lane quarter of this warp
         const int row = quad * 32 + lane;                            // row inside a 128-row tile
         const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16);
         const float c2 = d.scale * 1.4426950408889634f;
         const uint64_t c2x2 = pack2(c2, c2);
-        const int rl = NR == 2 ? wg : 0;                             // local row tile of this warpgroup
-        const int rp0 = (rt0 + rl) * 128;                            // its first packed row
-        const bool warp_valid = rp0 + quad * 32 < R;                 // warp-uniform: any live row in this warp
-        const uint32_t o_addr = lane_addr + COL_O + wg * 128;
-        float m_ref = -INFINITY, l = 0.f;                            // this thread's row, this warpgroup's key subset
-        const int n_pairs = n_steps >> 1;
-        for (int p = 0; p < n_pairs && !LS_DBG(8); ++p) {
-            const int t = 2 * p + wg;                                // this warpgroup's step of the pair
-            const int bi = t & 3;
-            const int j = NR == 2 ? p >> 1 : p;                      // key tile
-            const int h = NR == 2 ? p & 1 : wg;                      // 64-key half of the tile
-            mbar_wait(bar(B_S_FULL + (p & 1)), (p >> 1) & 1);
-            if (!warp_valid || LS_DBG(4)) {
-                // padding rows only: keep the barrier protocol, skip the math (their O rows are never read)
-                mbar_arrive(bar(B_P_FULL + (p & 1)));
-                continue;
-            }
-            tc_fence_after();
-            if (quad == 0 && lane == 0) LS_TRACE(2, t);
-            const uint32_t buf = lane_addr + COL_SP + bi * 64;
-            uint32_t sv[64];
-            LS_TMEM_LD32(buf, sv);
-            LS_TMEM_LD32(buf + 32, (sv + 32));
-            tmem_wait_ld();
-            if (quad == 0 && lane == 0) LS_TRACE(3, t);
-            const int gi = tile_index(j);
-            if (gi >= total_tiles) {
-                // per-row visibility word of this half's 64 key slots
-                const SpecialTile st = sp_tiles[gi - total_tiles];
-                const int rp = rp0 + row;
-                uint64_t vis = 0ull;
-                if (rp < R) {
-                    const int qi = rp / G;
-                    if (st.kind == 0) {
-                        const int hi = d.causal ? kv_len - (n_q - 1 - qi) : kv_len;      // visible global keys: key < hi
-                        const int cnt = min(max(hi - st.base, 0), st.n_valid) - h * 64;
-                        vis = cnt >= 64 ? ~0ull : (cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull));
-                    } else {
-                        const uint64_t* w = d.tail_mask + static_cast<size_t>(qi) * LS_MASK_WORDS;
-                        const int k0 = st.base + h * 64;
-                        const int wi = k0 >> 6, sh = k0 & 63;
-                        if (wi < LS_MASK_WORDS) {
-                            vis = w[wi] >> sh;
-                            if (sh && wi + 1 < LS_MASK_WORDS) vis |= w[wi + 1] << (64 - sh);
+        float* xch = reinterpret_cast<float*>(smem + OFF_STATE);     // [2 warpgroups][128 rows] exchange scratch
+        const int n_pairs = n_tiles * NR;
+        float m_ref0 = -INFINITY, m_ref1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // per local row tile
+        int j = 0, r = 0;
+        for (int p = 0; p < n_pairs; ++p) {
+            const int pb = p & 1;
+            const int rp0 = (rt0 + r) * 128;
+            const bool warp_valid = rp0 + quad * 32 < R;             // the same for both warps of a quarter
+            mbar_wait(bar(B_S_FULL + pb), (p >> 1) & 1);
+            if (warp_valid) {
+                tc_fence_after();
+                if (quad == 0 && lane == 0) LS_TRACE(2, 2 * p + wg);
+                const uint32_t buf = lane_addr + COL_SP + pb * 128 + wg * 64;
+                uint32_t sv[64];
+                LS_TMEM_LD32(buf, sv);
+                LS_TMEM_LD32(buf + 32, (sv + 32));
+                tmem_wait_ld();
+                if (quad == 0 && lane == 0) LS_TRACE(3, 2 * p + wg);
+                const int gi = tile_index(j);
+                if (gi >= total_tiles) {
+                    // per-row visibility word of this half's 64 key slots
+                    const SpecialTile st = sp_tiles[gi - total_tiles];
+                    const int rp = rp0 + row;
+                    uint64_t vis = 0ull;
+                    if (rp < R) {
+                        const int qi = rp / G;
+                        if (st.kind == 0) {
+                            const int hi = d.causal ? kv_len - (n_q - 1 - qi) : kv_len;      // visible global keys: key < hi
+                            const int cnt = min(max(hi - st.base, 0), st.n_valid) - wg * 64;
+                            vis = cnt >= 64 ? ~0ull : (cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull));
+                        } else {
+                            const uint64_t* w = d.tail_mask + static_cast<size_t>(qi) * LS_MASK_WORDS;
+                            const int k0 = st.base + wg * 64;
+                            const int wi = k0 >> 6, sh = k0 & 63;
+                            if (wi < LS_MASK_WORDS) {
+                                vis = w[wi] >> sh;
+                                if (sh && wi + 1 < LS_MASK_WORDS) vis |= w[wi + 1] << (64 - sh);
+                            }
+                            const int cnt = st.n_valid - wg * 64;
+                            if (cnt < 64) vis &= cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull);
                         }
-                        const int cnt = st.n_valid - h * 64;
-                        if (cnt < 64) vis &= cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull);
                     }
+#pragma unroll
+                    for (int e = 0; e < 64; ++e)
+                        if (!((vis >> e) & 1ull)) sv[e] = 0xff800000u;                       // -inf
                 }
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                for (int e = 0; e < 64; ++e)
-                    if (!((vis >> e) & 1ull)) sv[e] = 0xff800000u;                       // -inf
-            }
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+                for (int e = 0; e < 64; e += 8) {
+                    mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])));
+                    mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])));
+                    mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sv[e + 4]), __uint_as_float(sv[e + 5])));
+                    mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sv[e + 6]), __uint_as_float(sv[e + 7])));
+                }
+                const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c2;
+                float m_ref = r == 0 ? m_ref0 : m_ref1;
+                // does ANY row of this lane quarter (either half) have to move its reference?  (named barrier 2 + quad,
+                // the 64 threads of the two warps that share the quarter)
+                uint32_t any;
+                {
+                    const uint32_t need = mx > m_ref + 8.0f ? 1u : 0u;   // lazy rescale threshold (2^8)
+                    asm volatile(
+                        "{\n\t"
+                        ".reg .pred pin, pout;\n\t"
+                        "setp.ne.u32 pin, %1, 0;\n\t"
+                        "bar.red.or.pred pout, %2, 64, pin;\n\t"
+                        "selp.u32 %0, 1, 0, pout;\n\t"
+                        "}" : "=r"(any) : "r"(need), "r"(2 + quad) : "memory");
+                }
+                if (any) {
+                    xch[wg * 128 + row] = mx;
+                    asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");
+                    const float joint = fmaxf(mx, xch[(wg ^ 1) * 128 + row]);
+                    const float m_new = joint > m_ref + 8.0f ? joint : m_ref;   // the same decision in both threads of the row
+                    const float alpha = m_ref == -INFINITY ? 0.f : fast_exp2(m_ref - m_new);   // nothing accumulated yet: 0 (never exp2(-inf + inf)); 1 if unchanged
+                    if (r == 0) l0 *= alpha; else l1 *= alpha;
+                    m_ref = m_new;
+                    if (p >= NR) {
+                        // The accumulator is quiescent once PV(p - NR) completed.  S_FULL(p) certifies every MMA issued
+                        // before QK(p), i.e. PV(p-2) and older; with one row tile PV(p-1) is certified by S_FULL(p+1),
+                        // this thread's next wait anyway (its previous phase completed long ago: no parity aliasing).
+                        if (NR == 1) mbar_wait(bar(B_S_FULL + ((p + 1) & 1)), ((p + 1) >> 1) & 1);
+                        tc_fence_after();
+                        const uint32_t o_half = lane_addr + COL_O + r * 128 + wg * 64;
 #pragma unroll
-            for (int e = 0; e < 64; e += 8) {
-                mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])));
-                mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])));
-                mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sv[e + 4]), __uint_as_float(sv[e + 5])));
-                mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sv[e + 6]), __uint_as_float(sv[e + 7])));
-            }
-            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c2;
-            const bool need = mx > m_ref + 8.0f;                     // lazy rescale threshold (2^8)
-            if (__any_sync(0xffffffffu, need)) {
-                const float m_new = need ? mx : m_ref;
-                const float alpha = m_ref == -INFINITY ? 0.f : fast_exp2(m_ref - m_new);   // nothing accumulated yet: 0, never exp2(-inf + inf)
-                l *= alpha;
-                m_ref = m_new;
-                if (p >= 1) {
-                    // This accumulator is quiescent once PV(pair p-1) completed, which the commit of iteration p-1 - the
-                    // S_FULL of pair p+1, this warpgroup's next wait anyway - certifies.  That barrier's previous phase
-                    // (pair p-1) completed long ago, so the parity wait cannot alias.
-                    mbar_wait(bar(B_S_FULL + ((p + 1) & 1)), ((p + 1) >> 1) & 1);
-                    tc_fence_after();
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t ov[32];
+                            LS_TMEM_LD32(o_half + c * 32, ov);
+                            tmem_wait_ld();
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t ov[32];
-                        LS_TMEM_LD32(o_addr + c * 32, ov);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
-                        LS_TMEM_ST32(o_addr + c * 32, ov);
+                            for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+                            LS_TMEM_ST32(o_half + c * 32, ov);
+                        }
+                        tmem_wait_st();
+                        tc_fence_before();
                     }
-                    tmem_wait_st();
-                    tc_fence_before();
+                    if (r == 0) m_ref0 = m_ref; else m_ref1 = m_ref;
+                    asm volatile("bar.sync %0, 64;" ::"r"(2 + quad) : "memory");   // xch is reused by the next exchange
                 }
-            }
-            // p = 2^(s * c2 - m_ref), packed fp32x2 FMA / ADD
-            const float m_use = m_ref == -INFINITY ? 0.f : m_ref;      // row with no visible key so far: p = 2^(-inf) = 0
-            const uint64_t negm = pack2(-m_use, -m_use);
-            uint64_t sum_a = 0ull, sum_b = 0ull;                     // {0.f, 0.f}
-            uint32_t pk[32];
+                // p = 2^(s * c2 - m_ref), packed fp32x2 FMA / ADD
+                const float m_use = m_ref == -INFINITY ? 0.f : m_ref;      // row with no visible key so far: p = 2^(-inf) = 0
+                const uint64_t negm = pack2(-m_use, -m_use);
+                uint64_t sum_a = 0ull, sum_b = 0ull;                     // {0.f, 0.f}
+                uint32_t pk[32];
 #pragma unroll
-            for (int e = 0; e < 64; e += 4) {
-                float x0, x1, x2, x3;
-                unpack2(fma2(pack2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), c2x2, negm), x0, x1);
-                unpack2(fma2(pack2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), c2x2, negm), x2, x3);
-                const float p0 = fast_exp2(x0), p1 = fast_exp2(x1), p2 = fast_exp2(x2), p3 = fast_exp2(x3);
-                sum_a = add2(sum_a, pack2(p0, p1));
-                sum_b = add2(sum_b, pack2(p2, p3));
-                pk[e >> 1] = Num<T>::pack(p0, p1);
-                pk[(e >> 1) + 1] = Num<T>::pack(p2, p3);
+                for (int e = 0; e < 64; e += 4) {
+                    float x0, x1, x2, x3;
+                    unpack2(fma2(pack2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), c2x2, negm), x0, x1);
+                    unpack2(fma2(pack2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), c2x2, negm), x2, x3);
+                    const float p0 = fast_exp2(x0), p1 = fast_exp2(x1), p2 = fast_exp2(x2), p3 = fast_exp2(x3);
+                    sum_a = add2(sum_a, pack2(p0, p1));
+                    sum_b = add2(sum_b, pack2(p2, p3));
+                    pk[e >> 1] = Num<T>::pack(p0, p1);
+                    pk[(e >> 1) + 1] = Num<T>::pack(p2, p3);
+                }
+                {
+                    float a0, a1;
+                    unpack2(add2(sum_a, sum_b), a0, a1);
+                    if (r == 0) l0 += a0 + a1; else l1 += a0 + a1;
+                }
+                // P -> in place over the first 32 columns of this half's S columns
+                if (quad == 0 && lane == 0) LS_TRACE(4, 2 * p + wg);
+                LS_TMEM_ST32(buf, pk);
+                tmem_wait_st();
+                tc_fence_before();
             }
-            {
-                float a0, a1;
-                unpack2(add2(sum_a, sum_b), a0, a1);
-                l += a0 + a1;
-            }
-            // P -> in place over the S tile it came from (A operand of the PV MMA, 2 values per 32-bit column)
-            if (quad == 0 && lane == 0) LS_TRACE(4, t);
-            LS_TMEM_ST32(buf, pk);
-            tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive(bar(B_P_FULL + (p & 1)));
-            if (quad == 0 && lane == 0) LS_TRACE(5, t);
+            mbar_arrive(bar(B_P_FULL + pb));
+            if (quad == 0 && lane == 0) LS_TRACE(5, 2 * p + wg);
+            if (++r == NR) { r = 0; ++j; }
         }
         // ================= epilogue: normalised partial O + LSE =================
         const int Rtot = d.q_rows * G;
         const int nr_out = min(NRS - rt0, NRL_MAX);                 // row tiles this CTA is responsible for
-        if (n_steps > 0) {
+        if (n_pairs > 0) {
             mbar_wait(bar(B_ALL_DONE), 0);           // single-phase barrier: no parity aliasing
             tc_fence_after();
         }
         auto part_base = [&](int sl, int rp) { return (static_cast<size_t>(d.part_offset + sl) * d.n_kv_heads + kvh) * Rtot + rp; };
-        if (NR == 2) {
-            // warpgroup = row tile: (m_ref, l) and the accumulator are complete as they stand
-            const int rp = rp0 + row;
-            const float inv = l > 0.f ? 1.f / l : 0.f;
+        // total row sums: the two warpgroups hold partial sums over their key halves relative to the SAME reference
+        float* xl = xch;                                             // [2 row tiles][2 warpgroups][128]: reuse after a full sync
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        xl[(0 * 2 + wg) * 128 + row] = l0;
+        xl[(1 * 2 + wg) * 128 + row] = l1;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int re = 0; re < nr_out; ++re) {
+            const bool live = n_pairs > 0 && re < NR;
+            const int rp = (rt0 + re) * 128 + row;
+            const float lt = xl[(re * 2) * 128 + row] + xl[(re * 2 + 1) * 128 + row];
+            const float m_ref = re == 0 ? m_ref0 : m_ref1;
+            const float inv = (live && lt > 0.f) ? 1.f / lt : 0.f;
             const size_t base = part_base(slot, rp);
-            if (rp < R) d.part_lse[base] = inv > 0.f ? (m_ref + log2f(l)) * 0.6931471805599453f : -INFINITY;
-            if (warp_valid) {                             // warp-uniform (tcgen05.ld is warp-collective)
+            if (wg == 0 && rp < R) {
+                d.part_lse[base] = inv > 0.f ? (m_ref + log2f(lt)) * 0.6931471805599453f : -INFINITY;
+                if (empty_slot >= 0) d.part_lse[part_base(empty_slot, rp)] = -INFINITY;
+            }
+            if ((rt0 + re) * 128 + quad * 32 < R) {   // warp-uniform (tcgen05.ld is warp-collective)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
+                    const int col = wg * 64 + c * 32;
                     uint32_t ov[32];
-                    if (n_steps > 0) {
-                        LS_TMEM_LD32(o_addr + c * 32, ov);
+                    if (live) {
+                        LS_TMEM_LD32(lane_addr + COL_O + re * 128 + col, ov);
                         tmem_wait_ld();
                     }
-                    if (inv == 0.f) {                     // no key seen (or no tile at all): the accumulator holds stale bits
+                    if (inv == 0.f) {                 // no key seen (or no tile at all): the accumulator holds stale bits
 #pragma unroll
                         for (int e = 0; e < 32; ++e) ov[e] = 0u;
                     }
                     if (rp < R) {
-                        float* po = d.part_o + base * 128 + c * 32;
+                        float* po = d.part_o + base * 128 + col;
 #pragma unroll
                         for (int e = 0; e < 32; e += 4)
                             *reinterpret_cast<float4*>(po + e) =
                                 make_float4(__uint_as_float(ov[e]) * inv, __uint_as_float(ov[e + 1]) * inv,
                                             __uint_as_float(ov[e + 2]) * inv, __uint_as_float(ov[e + 3]) * inv);
-                    }
-                }
-            }
-        } else {
-            // One (or no) live row tile: the two warpgroups hold partial states of the SAME rows over alternate key
-            // halves.  Exchange (m, l) through shared memory, then each warpgroup merges and writes 64 of the 128
-            // output columns.  Row tiles without live rows / CTAs without keys write empty partials.
-            st_m[wg * 128 + row] = m_ref;
-            st_l[wg * 128 + row] = l;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float m0 = st_m[row], m1 = st_m[128 + row], l0 = st_l[row], l1 = st_l[128 + row];
-            const float m = fmaxf(m0, m1);
-            const float a0 = l0 > 0.f ? fast_exp2(m0 - m) : 0.f, a1 = l1 > 0.f ? fast_exp2(m1 - m) : 0.f;
-            const float lt = l0 * a0 + l1 * a1;
-            const float inv = lt > 0.f ? 1.f / lt : 0.f;
-            const float w0 = a0 * inv, w1 = a1 * inv;
-            for (int re = 0; re < nr_out; ++re) {
-                const bool live = re == 0 && NR == 1 && n_steps > 0;
-                const int rp = (rt0 + re) * 128 + row;
-                const size_t base = part_base(slot, rp);
-                if (wg == 0 && rp < R) {
-                    d.part_lse[base] = (live && inv > 0.f) ? (m + log2f(lt)) * 0.6931471805599453f : -INFINITY;
-                    if (empty_slot >= 0) d.part_lse[part_base(empty_slot, rp)] = -INFINITY;
-                }
-                if ((rt0 + re) * 128 + quad * 32 < R) {   // warp-uniform
+                        if (empty_slot >= 0) {
+                            float* pe = d.part_o + part_base(empty_slot, rp) * 128 + col;
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int col = wg * 64 + c * 32;
-                        uint32_t o0[32], o1[32];
-                        if (live) {
-                            LS_TMEM_LD32(lane_addr + COL_O + col, o0);
-                            LS_TMEM_LD32(lane_addr + COL_O + 128 + col, o1);
-                            tmem_wait_ld();
-                        }
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            // an accumulator that never received a PV holds stale TMEM bits: select, do not multiply
-                            const float x0 = (live && w0 > 0.f) ? __uint_as_float(o0[e]) * w0 : 0.f;
-                            const float x1 = (live && w1 > 0.f) ? __uint_as_float(o1[e]) * w1 : 0.f;
-                            o0[e] = __float_as_uint(x0 + x1);
-                        }
-                        if (rp < R) {
-                            float* po = d.part_o + base * 128 + col;
-#pragma unroll
-                            for (int e = 0; e < 32; e += 4)
-                                *reinterpret_cast<float4*>(po + e) = make_float4(__uint_as_float(o0[e]), __uint_as_float(o0[e + 1]),
-                                                                                __uint_as_float(o0[e + 2]), __uint_as_float(o0[e + 3]));
-                            if (empty_slot >= 0) {
-                                float* pe = d.part_o + part_base(empty_slot, rp) * 128 + col;
-#pragma unroll
-                                for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(pe + e) = make_float4(0.f, 0.f, 0.f, 0.f);
-                            }
+                            for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(pe + e) = make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                     }
                 }
