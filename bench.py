@@ -355,8 +355,11 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT,
                 "h2d_bytes_per_step": ids_host.numel() * 8 / (W + K), "d2h_bytes_per_step": 16 + out_host.numel() * 8 / (W + K),
+                "ms_per_step": float(e2e_t) * 1e3 / K, "accepted_len_tau": e2e_tokens / K,
                 "note": "LlamaGlide.tree_spec_generate with a pinned host prompt; last K rounds of the call, each with its "
-                        "device->host read of the accept/stop counters; prefill excluded like the reference's elapsed_time"},
+                        "device->host read of the accept/stop counters; prefill excluded like the reference's elapsed_time. "
+                        "These are different rounds of the generation than the replayed ones behind `value`, so the "
+                        "accepted length differs: compare ms_per_step for the host-loop overhead"},
         "gpu_launches": int(launches_per_round * K),
         "roofline": roofline,
         "cpu_baseline": cpu,
