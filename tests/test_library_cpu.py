@@ -125,3 +125,55 @@ def test_checkpoint_directories_load_with_the_reference_key_names(tmp_path):
         assert torch.equal(got[k], sd[k]), k
     with pytest.raises(FileNotFoundError):
         _load_dir(str(tmp_path / "missing"))
+
+
+def _tc_roles(n_slots, nrs, all_tiles):
+    """Host-side mirror of the role / tile assignment of attn_tc_kernel (attn_tc.cu, "role of this CTA"): returns one
+    dict per CTA of a kv head.  Kept next to the kernel's integer logic as an executable statement of its contract."""
+    nrl_max = 2
+    grid_x = n_slots + (n_slots + 1) // 2 if nrs > nrl_max else n_slots
+    per = (all_tiles + n_slots - 1) // n_slots
+    ctas = []
+    for bx in range(grid_x):
+        slot, rt0, share0, nshare, first, empty_slot = bx, 0, bx, 1, 0, -1
+        if nrs > nrl_max:
+            light = bx >= n_slots
+            g = bx - n_slots if light else bx >> 1
+            share0 = 2 * g
+            nshare = min(2, n_slots - share0)
+            if light:
+                slot, rt0, empty_slot = share0, nrl_max, (share0 + 1 if nshare == 2 else -1)
+            else:
+                first = bx & 1
+        stride = nshare if (nrs > nrl_max and rt0 == 0) else 1
+        lo = min(share0 * per, all_tiles) + first
+        hi = min((share0 + nshare) * per, all_tiles)
+        tiles = list(range(lo, hi, stride)) if hi > lo else []
+        rows = list(range(rt0, min(nrs, rt0 + nrl_max)))
+        ctas.append(dict(slot=slot, rows=rows, tiles=tiles, empty_slot=empty_slot))
+    return ctas
+
+
+@pytest.mark.parametrize("nrs", [1, 2, 3])
+def test_tc_kernel_role_assignment_covers_every_tile_and_slot_once(nrs):
+    """Every (key tile, row tile) is processed by exactly one CTA, and every (partial slot, row tile) has exactly one
+    writer (a real one or the light CTA's explicit empty partial) - the contract ls_attn_combine relies on."""
+    for n_slots in range(1, 20):
+        for all_tiles in (0, 1, 2, 3, 7, 12, 13, 64, 1031):
+            ctas = _tc_roles(n_slots, nrs, all_tiles)
+            seen, writers = {}, {}
+            for c in ctas:
+                for r in c["rows"]:
+                    writers[(c["slot"], r)] = writers.get((c["slot"], r), 0) + 1
+                    if c["empty_slot"] >= 0:
+                        writers[(c["empty_slot"], r)] = writers.get((c["empty_slot"], r), 0) + 1
+                    for t in c["tiles"]:
+                        seen[(t, r)] = seen.get((t, r), 0) + 1
+            assert all(v == 1 for v in seen.values())
+            assert set(seen) == {(t, r) for t in range(all_tiles) for r in range(nrs)}
+            assert writers == {(s, r): 1 for s in range(n_slots) for r in range(nrs)}, (n_slots, nrs, all_tiles)
+            if nrs == 3:     # trios are balanced: a light CTA runs as many (tile, row tile) steps as each of its heavy CTAs (+-1 tile)
+                for c in ctas:
+                    if c["rows"] == [2] and c["empty_slot"] >= 0:
+                        heavy = [h for h in ctas if h["rows"] == [0, 1] and h["slot"] in (c["slot"], c["empty_slot"])]
+                        assert all(abs(2 * len(h["tiles"]) - len(c["tiles"])) <= 1 for h in heavy)
