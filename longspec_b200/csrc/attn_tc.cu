@@ -3,30 +3,33 @@
 // Work unit: one CTA = (kv head, a share of the 128-key tiles, up to TWO row tiles of 128 packed query rows),
 // a packed row being r = token * G + head-in-group, so a K/V tile serves the whole GQA group and candidate tree.
 //
-// TMEM (512 columns) = four 64-column S/P buffers + two 128-column O accumulators - the FA4 shape.  A STEP is
-// (key tile, 64-key half, row tile); step t lives in S/P buffer t & 3 and accumulates into O accumulator t & 1,
-// which softmax warpgroup t & 1 owns together with the (m, l) row state in REGISTERS.  Two row tiles: one
-// warpgroup + accumulator per row tile.  One row tile: the warpgroups take alternate key halves into two
-// accumulators and the epilogue merges the two partial states.  Four buffers = four QK -> softmax -> PV chains in
-// flight; the measured limiter is shared-memory operand bandwidth.
+// TMEM (512 columns) = two 128-column S/P buffers + two 128-column O accumulators - the FA4 shape.  A PAIR is
+// (key tile, row tile): ONE S = Q K^T with N = 128 keys (tensor-rate; the N = 64 form of round 1 was bound by
+// shared-memory operand bandwidth), one softmax pass, ONE O += P V with K = 128 keys.  Pair p lives in S/P buffer
+// p & 1, accumulates into O accumulator p & 1, and belongs to softmax warpgroup p & 1, which keeps the (m, l) row
+// state in REGISTERS and never shares it.  Two row tiles: pair p = (key tile p >> 1, row tile p & 1), i.e. one
+// warpgroup + accumulator per row tile.  One row tile: pair p = key tile p, the warpgroups take alternate key
+// tiles into two accumulators and the epilogue merges the two partial states.
 // A call with three row tiles (the Llama-3 verify shape: 74 tokens x GQA-4 = 296 rows) is cut into "trios": two
 // HEAVY CTAs (row tiles 0-1, alternate key tiles of the group's range) and one LIGHT CTA (row tile 2, every key
-// tile of the range).  All three run the same number of steps, and the light CTA's K/V loads hit L2 behind the
+// tile of the range).  All three run the same number of pairs, and the light CTA's K/V loads hit L2 behind the
 // heavy CTAs' loads, so HBM still sees every byte once (ncu: dram bytes = algorithmic bytes).
 //
 //   warp 0              TMA producer: 128-key K and V tiles (2 x [128 x 128 B] boxes each, SWIZZLE_128B) from the
 //                       paged pool into separate 2-stage K and V rings, completion on mbarriers
-//   warp 1              MMA issuer (converged warp, one elected lane): S = Q K^T (M128 N64 K16 x8, SS) and
-//                       O += P V (M128 N128 K16 x4, TS: P read from TMEM, V MN-major in smem), issued in PAIRS of
-//                       steps:  QK(pair 0) QK(pair 1) | P(0): PV(0) QK(2) | P(1): PV(1) QK(3) | ...
-//                       MMAs of one thread execute in issue order, so QK(pair p+2) cannot overwrite the buffers
-//                       PV(pair p) still reads: no "buffer free" barriers.  tcgen05.mma issue is throttled to the
-//                       pipe's execution rate, so the issuer does one wait and one commit per 24 MMAs.
+//   warp 1              MMA issuer (converged warp, one elected lane): S = Q K^T (M128 N128 K16 x8, SS) and
+//                       O += P V (M128 N128 K16 x8, TS: P read from TMEM, V MN-major in smem):
+//                         QK(0) QK(1) | P(0) ready: PV(0) QK(2) | P(1) ready: PV(1) QK(3) | ...
+//                       MMAs of one thread execute in issue order, so QK(p+2) cannot overwrite the buffer PV(p)
+//                       still reads: no "buffer free" barriers, one wait and one commit per 16 MMAs.
 //   warp 2              TMEM allocation
-//   warps 4-7 / 8-11    two softmax warpgroups, one step of every pair each.  One row per thread: tcgen05.ld the
-//                       64-key S tile, online softmax in the log2 domain with lazy rescaling (O in TMEM is only
-//                       rescaled when a row maximum grows by more than 2^8), P rounded to dtype and tcgen05.st IN
-//                       PLACE over the first 32 columns of the S buffer it came from (S and P alias).
+//   warps 4-7 / 8-11    two softmax warpgroups (setmaxnreg 216; warps 0-3 drop to 72).  One row per thread:
+//                       tcgen05.ld the 128-key S tile, online softmax in the log2 domain with lazy rescaling (O in
+//                       TMEM is only rescaled when a row maximum grows by more than 2^8), P rounded to dtype and
+//                       tcgen05.st IN PLACE over the first 64 columns of the S buffer it came from.  The kernel sits
+//                       where MUFU (16 ex2/clk/SM) and the tensor pipe cost the same per tile, so LS_TC_POLY of
+//                       every 8 exponentials are computed on the FMA pipe instead (Cody-Waite + cubic, rel. error
+//                       2^-13.2 - below the rounding of P to bf16/fp16; tools/ubench/softmax_math.cu).
 // The masked remainder of the call (last partial prefix tile, causal rows, the tree-masked tail = this round's
 // tokens) is appended to the tile sequence as "special tiles" whose softmax applies a per-row bit mask, so one
 // launch covers the whole attention call.  The epilogue writes normalised partial O (fp32) and the natural-log
@@ -65,8 +68,8 @@ constexpr int OFF_SPECIAL = OFF_BAR + BAR_BYTES;
 constexpr int SMEM_BYTES = OFF_SPECIAL + SPECIAL_BYTES + 1024;   // + worst-case alignment of the dynamic base
 
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t COL_SP = 0;                     // four buffers of 64 columns: a 128 x 64 fp32 score tile, overwritten
-                                                   // in place by its 128 x 64 bf16/fp16 probability tile (32 columns)
+constexpr uint32_t COL_SP = 0;                     // two buffers of 128 columns: a 128 x 128 fp32 score tile, overwritten
+                                                   // in place by its 128 x 128 bf16/fp16 probability tile (64 columns)
 constexpr uint32_t COL_O = 256;                    // 2 x 128
 
 constexpr int MAX_SPECIAL = 12;
@@ -77,8 +80,8 @@ struct SpecialTile {
     int base;     // kind 0: global index of key 0;  kind 1: tail index of key 0
 };
 
-// S_FULL / P_FULL are indexed by pair parity (pair p = steps 2p, 2p+1).  Every barrier is waited on phase by phase
-// by its waiter (or provably at most one phase behind), so mbarrier parity waits can never alias.
+// S_FULL / P_FULL are indexed by pair parity (= softmax warpgroup).  Every barrier is waited on phase by phase by its
+// waiter, so mbarrier parity waits can never alias.
 enum { B_K_FULL = 0, B_K_EMPTY = 2, B_V_FULL = 4, B_V_EMPTY = 6, B_S_FULL = 8, B_P_FULL = 10, B_ALL_DONE = 12, B_COUNT = 13 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -225,6 +228,91 @@ __device__ long long* g_trace = nullptr;
 #define LS_DBG(bit) 0
 #endif
 
+// 16-register flavour of the TMEM store (one 32-key slice of P = 16 packed columns)
+#define LS_TMEM_ST16(taddr, v)                                                                                       \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"   \
+                 "%16};"                                                                                              \
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),           \
+                   "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),        \
+                   "r"(v[15])                                                                                         \
+                 : "memory")
+
+// Register budget (setmaxnreg works per warpgroup): warps 0-3 (TMA, MMA issue, TMEM allocation) give registers back,
+// the two softmax warpgroups hold a whole 128-key score row per thread.  setmaxnreg only moves registers inside the
+// pool the CTA was LAUNCHED with (384 threads x 168 registers = 64512, not the SM's 65536): a request beyond it blocks
+// forever, so 128 * REGS_CTRL + 256 * REGS_SOFTMAX must not exceed THREADS * 168.
+constexpr int REGS_LAUNCH = 168;                   // __launch_bounds__(384, 1)
+constexpr int REGS_CTRL = 72;
+constexpr int REGS_SOFTMAX = 216;
+static_assert(128 * REGS_CTRL + 256 * REGS_SOFTMAX <= THREADS * REGS_LAUNCH, "setmaxnreg budget exceeds the CTA's register pool");
+static_assert(REGS_CTRL % 8 == 0 && REGS_SOFTMAX % 8 == 0, "setmaxnreg takes multiples of 8");
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// How many of every 8 exponentials leave the MUFU pipe for the FMA pipe (tools/ubench/softmax_math.cu: 2 of 8 is the
+// measured optimum: 868 instead of 1049 cycles per 128 x 128 tile).  Must be even (the polynomial works on pairs).
+#ifndef LS_TC_POLY
+#define LS_TC_POLY 2
+#endif
+static_assert(LS_TC_POLY >= 0 && LS_TC_POLY <= 8 && LS_TC_POLY % 2 == 0, "LS_TC_POLY must be 0, 2, 4, 6 or 8");
+
+// 2^x for a packed pair on the FMA pipe.  x = n + f with n = round(x) (the 1.5 * 2^23 trick leaves n in the low
+// mantissa bits of t), f in [-1/2, 1/2]; 2^f by a cubic (Chebyshev fit, max relative error 2^-13.2); the result is
+// assembled by adding n to the exponent field.  Inputs are clamped at -126 (anything below is 0 after rounding to P's
+// 16-bit type anyway: 2^-126 * 2^8 is far below the smallest bf16/fp16 a row sum can see).
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
+    constexpr float MAGIC = 12582912.f;
+    float x0, x1;
+    unpack2(x2, x0, x1);
+    x0 = fmaxf(x0, -126.f);
+    x1 = fmaxf(x1, -126.f);
+    x2 = pack2(x0, x1);
+    const uint64_t t2 = add2(x2, pack2(MAGIC, MAGIC));
+    const uint64_t n2 = add2(t2, pack2(-MAGIC, -MAGIC));
+    const uint64_t f2 = fma2(n2, pack2(-1.f, -1.f), x2);
+    uint64_t q2 = fma2(f2, pack2(0.05592204f, 0.05592204f), pack2(0.24264008f, 0.24264008f));
+    q2 = fma2(q2, f2, pack2(0.69312102f, 0.69312102f));
+    q2 = fma2(q2, f2, pack2(0.99992448f, 0.99992448f));
+    float q0, q1, t0, t1;
+    unpack2(q2, q0, q1);
+    unpack2(t2, t0, t1);
+    p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+    p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+
+// The exponential phase of one 128-key score row: p = 2^(s * c2 - m), packed fp32x2 FMA / ADD, POLY of every 8
+// exponentials on the FMA pipe and the rest on MUFU; P is rounded to the 16-bit type and stored to TMEM (A operand of
+// the PV MMA, 2 values per 32-bit column) one 32-key slice at a time.  Returns the row sum of the unrounded p.
+template <typename T, int POLY>
+__device__ __forceinline__ float exp_phase(const uint32_t (&sv)[128], uint32_t buf, uint64_t c2x2, uint64_t negm) {
+    uint64_t sum_a = 0ull, sum_b = 0ull;                     // {0.f, 0.f}
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+            const uint64_t x2 = fma2(pack2(__uint_as_float(sv[c * 32 + e]), __uint_as_float(sv[c * 32 + e + 1])), c2x2, negm);
+            float p0, p1;
+            if ((e & 7) < POLY) {
+                exp2_poly2(x2, p0, p1);
+            } else {
+                float x0, x1;
+                unpack2(x2, x0, x1);
+                p0 = fast_exp2(x0);
+                p1 = fast_exp2(x1);
+            }
+            if (e & 2) sum_b = add2(sum_b, pack2(p0, p1)); else sum_a = add2(sum_a, pack2(p0, p1));
+            pk[e >> 1] = Num<T>::pack(p0, p1);
+        }
+        LS_TMEM_ST16(buf + c * 16, pk);
+    }
+    float a0, a1;
+    unpack2(add2(sum_a, sum_b), a0, a1);
+    return a0 + a1;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
@@ -282,12 +370,9 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
     const int tile_lo = min(share0 * per, all_tiles) + first;
     const int tile_hi = min((share0 + nshare) * per, all_tiles);
     const int n_tiles = (NR > 0 && tile_hi > tile_lo) ? (tile_hi - tile_lo + stride - 1) / stride : 0;
-    // A step = (key tile j, 64-key half h, row tile r), in that nesting; step t runs on S/P buffer t & 3 and its PV
-    // accumulates into O accumulator t & 1, which softmax warpgroup t & 1 owns.  With two row tiles that is "one
-    // warpgroup and one accumulator per row tile"; with one row tile the two warpgroups take alternate key halves
-    // into two accumulators with private (m, l) row states, merged in the epilogue.
-    const int spt = 2 * NR;                                          // steps per key tile
-    const int n_steps = n_tiles * spt;
+    // Pair p = (key tile, row tile): NR == 2: (p >> 1, p & 1); NR == 1: (p, 0).  It runs in S/P buffer p & 1,
+    // accumulates into O accumulator p & 1 and is processed by softmax warpgroup p & 1.
+    const int n_pairs = n_tiles * NR;
     auto tile_index = [&](int j) { return tile_lo + j * stride; };   // position in the call's tile sequence
 
     float* st_m = reinterpret_cast<float*>(smem + OFF_STATE);        // epilogue exchange only (one row tile)
@@ -302,7 +387,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
             mbar_init(bar(B_K_FULL + i), 1); mbar_init(bar(B_K_EMPTY + i), 1);
             mbar_init(bar(B_V_FULL + i), 1); mbar_init(bar(B_V_EMPTY + i), 1);
         }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar(B_S_FULL + i), 1); mbar_init(bar(B_P_FULL + i), 256); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar(B_S_FULL + i), 1); mbar_init(bar(B_P_FULL + i), 128); }
         mbar_init(bar(B_ALL_DONE), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -311,7 +396,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     // Q tiles -> swizzled shared memory (K-major, SWIZZLE_128B): [tile][k-chunk][row][128B]
-    if (n_steps > 0) {
+    if (n_pairs > 0) {
         const T* __restrict__ q = reinterpret_cast<const T*>(d.q);
         const size_t q_stride = d.q_stride > 0 ? static_cast<size_t>(d.q_stride) : static_cast<size_t>(d.n_heads) * 128;
         for (int idx = tid; idx < NR * 128 * 16; idx += THREADS) {
@@ -334,114 +419,105 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
     const uint32_t tmem = *tmem_slot;
 
     constexpr int FMT = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
-    constexpr uint32_t IDESC_QK = make_idesc(128, 64, FMT, 0, 0);
+    constexpr uint32_t IDESC_QK = make_idesc(128, 128, FMT, 0, 0);
     constexpr uint32_t IDESC_PV = make_idesc(128, 128, FMT, 0, 1);
 
-    if (warp == 0) {
-        // ================= TMA producer (warp converged, one elected lane issues) =================
-        int s = 0, ph = 0;
-        for (int j = 0; j < n_tiles && !LS_DBG(16); ++j) {
-            const int gi = tile_index(j);
-            const int tok = gi >= total_tiles ? sp_tiles[gi - total_tiles].tok : gi * BN;
-            const int page = __ldg(d.page_table + (tok >> 7));
-            const int row = (page * d.n_kv_heads + kvh) * LS_PAGE + (tok & (LS_PAGE - 1));
-            mbar_wait(bar(B_K_EMPTY + s), ph ^ 1);
-            if (elect_one()) {
-                const uint32_t dst = sbase + OFF_K + s * TILE_BYTES;
-                mbar_expect_tx(bar(B_K_FULL + s), TILE_BYTES);
-                tma_load_2d(dst, &map_k, 0, row, bar(B_K_FULL + s));
-                tma_load_2d(dst + 16384, &map_k, 64, row, bar(B_K_FULL + s));
+    if (warp < 4) {
+        reg_dec<REGS_CTRL>();
+        if (warp == 0) {
+            // ================= TMA producer (warp converged, one elected lane issues) =================
+            int s = 0, ph = 0;
+            for (int j = 0; j < n_tiles && !LS_DBG(16); ++j) {
+                const int gi = tile_index(j);
+                const int tok = gi >= total_tiles ? sp_tiles[gi - total_tiles].tok : gi * BN;
+                const int page = __ldg(d.page_table + (tok >> 7));
+                const int row = (page * d.n_kv_heads + kvh) * LS_PAGE + (tok & (LS_PAGE - 1));
+                mbar_wait(bar(B_K_EMPTY + s), ph ^ 1);
+                if (elect_one()) {
+                    const uint32_t dst = sbase + OFF_K + s * TILE_BYTES;
+                    mbar_expect_tx(bar(B_K_FULL + s), TILE_BYTES);
+                    tma_load_2d(dst, &map_k, 0, row, bar(B_K_FULL + s));
+                    tma_load_2d(dst + 16384, &map_k, 64, row, bar(B_K_FULL + s));
+                }
+                __syncwarp();
+                mbar_wait(bar(B_V_EMPTY + s), ph ^ 1);
+                if (elect_one()) {
+                    const uint32_t dst = sbase + OFF_V + s * TILE_BYTES;
+                    mbar_expect_tx(bar(B_V_FULL + s), TILE_BYTES);
+                    tma_load_2d(dst, &map_v, 0, row, bar(B_V_FULL + s));
+                    tma_load_2d(dst + 16384, &map_v, 64, row, bar(B_V_FULL + s));
+                }
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1; }
             }
-            __syncwarp();
-            mbar_wait(bar(B_V_EMPTY + s), ph ^ 1);
-            if (elect_one()) {
-                const uint32_t dst = sbase + OFF_V + s * TILE_BYTES;
-                mbar_expect_tx(bar(B_V_FULL + s), TILE_BYTES);
-                tma_load_2d(dst, &map_v, 0, row, bar(B_V_FULL + s));
-                tma_load_2d(dst + 16384, &map_v, 64, row, bar(B_V_FULL + s));
-            }
-            __syncwarp();
-            if (++s == STAGES) { s = 0; ph ^= 1; }
-        }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        // The whole warp runs this loop converged (all values warp-uniform); one elected lane issues.
-        // Steps are issued in PAIRS (pair p = steps 2p, 2p+1 = one step of each softmax warpgroup); pair p lives in
-        // S/P buffers {0,1} (p even) or {2,3} (p odd).  In-order schedule:
-        //   QK(pair 0) QK(pair 1) | P(pair 0) ready: PV(pair 0) QK(pair 2) | P(pair 1) ready: PV(pair 1) QK(pair 3) | ...
-        // MMAs of one thread execute in issue order, so QK(pair p+2) cannot overwrite the buffers PV(pair p) still
-        // reads P from.  One commit per iteration: S_FULL of pair p+2, which also certifies PV(pair p) complete.
-        // (tcgen05.mma issue is throttled to the pipe's execution rate, so every instruction the issuing thread spends
-        // on barriers is tensor-pipe idle time - hence pairs: one wait and one commit per 24 MMAs.)
-        const uint32_t q_lo = (sbase >> 4) | LBO_K;
-        const uint32_t k_lo = ((sbase + OFF_K) >> 4) | LBO_K;
-        const uint32_t v_lo = ((sbase + OFF_V) >> 4) | LBO_V;
-        const int n_pairs = n_steps >> 1;
-        const int ppt = NR;                           // pairs per key tile
-        int pq = 0, iq = 0, sq = 0, phq = 0;          // next QK pair: index inside its key tile, K stage, K_FULL parity
-        int ip = 0, sp = 0, php = 0;                  // next PV pair: index inside its key tile, V stage, V_FULL parity
-        auto issue_qk_pair = [&]() {
-            if (iq == 0 && !LS_DBG(16)) mbar_wait(bar(B_K_FULL + sq), phq);
-            tc_fence_after();
-            if (elect_one()) {
-#pragma unroll
-                for (int s2 = 0; s2 < 2; ++s2) {
-                    const int h = NR == 2 ? iq : s2, r = NR == 2 ? s2 : 0;
-                    const uint32_t a0 = q_lo + r * (32768 >> 4), b0 = k_lo + sq * (TILE_BYTES >> 4) + h * (8192 >> 4);
-                    const uint32_t dst = tmem + COL_SP + ((2 * pq + s2) & 3) * 64;
+        } else if (warp == 1) {
+            // ================= MMA issuer =================
+            // The whole warp runs this loop converged (all values warp-uniform); one elected lane issues.
+            //   QK(0) QK(1) | P(0) ready: PV(0) QK(2) | P(1) ready: PV(1) QK(3) | ...
+            // MMAs of one thread execute in issue order, so QK(p+2) cannot overwrite the buffer PV(p) still reads P
+            // from.  One commit per iteration: S_FULL of pair p+2, which also certifies PV(p) - hence every earlier PV
+            // into the same accumulator - complete: the softmax warpgroup that sees S_FULL(p+2) may rescale O freely.
+            const uint32_t q_lo = (sbase >> 4) | LBO_K;
+            const uint32_t k_lo = ((sbase + OFF_K) >> 4) | LBO_K;
+            const uint32_t v_lo = ((sbase + OFF_V) >> 4) | LBO_V;
+            int pq = 0, rq = 0, sq = 0, phq = 0;          // next QK pair: index, row tile, K stage, K_FULL parity
+            int rp = 0, sp = 0, php = 0;                  // next PV pair: row tile, V stage, V_FULL parity
+            auto issue_qk = [&]() {
+                if (rq == 0 && !LS_DBG(16)) mbar_wait(bar(B_K_FULL + sq), phq);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a0 = q_lo + rq * (32768 >> 4), b0 = k_lo + sq * (TILE_BYTES >> 4);
+                    const uint32_t dst = tmem + COL_SP + (pq & 1) * 128;
                     if (!LS_DBG(2))
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk)
                         tc_mma2(dst, a0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2, b0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2,
                                 IDESC_QK, kk > 0 ? 1u : 0u);
+                    if (rq == NR - 1) tc_commit(bar(B_K_EMPTY + sq));
                 }
-                if (iq == ppt - 1) tc_commit(bar(B_K_EMPTY + sq));
+                __syncwarp();
+                ++pq;
+                if (++rq == NR) {
+                    rq = 0;
+                    if (++sq == STAGES) { sq = 0; phq ^= 1; }
+                }
+            };
+            for (int i = 0; i < 2 && i < n_pairs; ++i) {
+                issue_qk();
+                if (elect_one()) tc_commit(bar(B_S_FULL + i));
+                __syncwarp();
             }
-            __syncwarp();
-            ++pq;
-            if (++iq == ppt) {
-                iq = 0;
-                if (++sq == STAGES) { sq = 0; phq ^= 1; }
-            }
-        };
-        for (int i = 0; i < 2 && i < n_pairs; ++i) {
-            issue_qk_pair();
-            if (elect_one()) tc_commit(bar(B_S_FULL + i));
-            __syncwarp();
-        }
-        for (int p = 0; p < n_pairs; ++p) {
-            if (ip == 0 && !LS_DBG(16)) mbar_wait(bar(B_V_FULL + sp), php);
-            if (!LS_DBG(8)) mbar_wait(bar(B_P_FULL + (p & 1)), (p >> 1) & 1);
-            tc_fence_after();
-            if (lane == 0) LS_TRACE(0, p);
-            if (elect_one()) {
-#pragma unroll
-                for (int s2 = 0; s2 < 2; ++s2) {
-                    const int h = NR == 2 ? ip : s2;
-                    const uint32_t a0 = tmem + COL_SP + ((2 * p + s2) & 3) * 64, b0 = v_lo + sp * (TILE_BYTES >> 4) + h * (8192 >> 4);
-                    const uint32_t dst = tmem + COL_O + s2 * 128;
+            for (int p = 0; p < n_pairs; ++p) {
+                if (rp == 0 && !LS_DBG(16)) mbar_wait(bar(B_V_FULL + sp), php);
+                if (!LS_DBG(8)) mbar_wait(bar(B_P_FULL + (p & 1)), (p >> 1) & 1);
+                tc_fence_after();
+                if (lane == 0) LS_TRACE(0, p);
+                if (elect_one()) {
+                    const uint32_t a0 = tmem + COL_SP + (p & 1) * 128, b0 = v_lo + sp * (TILE_BYTES >> 4);
+                    const uint32_t dst = tmem + COL_O + (p & 1) * 128;
                     if (!LS_DBG(1))
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)      // 16 keys = 8 packed TMEM columns per K step
-                        tc_mma_ts(dst, a0 + kk * 8, b0 + kk * (2048 >> 4), IDESC_PV, (p > 0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < 8; ++kk)      // 16 keys = 8 packed TMEM columns per K step
+                        tc_mma_ts(dst, a0 + kk * 8, b0 + kk * (2048 >> 4), IDESC_PV, (p >= 2 || kk > 0) ? 1u : 0u);
+                    if (rp == NR - 1) tc_commit(bar(B_V_EMPTY + sp));
                 }
-                if (ip == ppt - 1) tc_commit(bar(B_V_EMPTY + sp));
+                __syncwarp();
+                if (++rp == NR) {
+                    rp = 0;
+                    if (++sp == STAGES) { sp = 0; php ^= 1; }
+                }
+                if (pq < n_pairs) issue_qk();
+                if (elect_one()) tc_commit(bar(B_S_FULL + (p & 1)));   // S of pair p+2 is ready / PV of pair p is complete
+                __syncwarp();
+                if (lane == 0) LS_TRACE(1, p);
             }
+            if (n_pairs > 0 && elect_one()) tc_commit(bar(B_ALL_DONE));   // every MMA of this CTA has completed once this fires
             __syncwarp();
-            if (++ip == ppt) {
-                ip = 0;
-                if (++sp == STAGES) { sp = 0; php ^= 1; }
-            }
-            if (pq < n_pairs) issue_qk_pair();
-            if (elect_one()) tc_commit(bar(B_S_FULL + (p & 1)));   // S of pair p+2 is ready / PV of pair p is complete
-            __syncwarp();
-            if (lane == 0) LS_TRACE(1, p);
         }
-        if (n_steps > 0 && elect_one()) tc_commit(bar(B_ALL_DONE));   // every MMA of this CTA has completed once this fires
-        __syncwarp();
-    } else if (warp >= 4) {
+    } else {
+        reg_inc<REGS_SOFTMAX>();
         // ================= softmax warpgroups =================
-        const int wg = (warp - 4) >> 2;                              // = step parity = O accumulator
+        const int wg = (warp - 4) >> 2;                              // = pair parity = S/P buffer = O accumulator
         const int quad = warp & 3;                                   // TMEM lane quarter of this warp
         const int row = quad * 32 + lane;                            // row inside a 128-row tile
         const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16);
@@ -451,58 +527,65 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         const int rp0 = (rt0 + rl) * 128;                            // its first packed row
         const bool warp_valid = rp0 + quad * 32 < R;                 // warp-uniform: any live row in this warp
         const uint32_t o_addr = lane_addr + COL_O + wg * 128;
-        float m_ref = -INFINITY, l = 0.f;                            // this thread's row, this warpgroup's key subset
-        const int n_pairs = n_steps >> 1;
-        for (int p = 0; p < n_pairs && !LS_DBG(8); ++p) {
-            const int t = 2 * p + wg;                                // this warpgroup's step of the pair
-            const int bi = t & 3;
+        const uint32_t buf = lane_addr + COL_SP + wg * 128;
+        float m_ref = -INFINITY, l = 0.f;                            // this thread's row, this warpgroup's pairs
+        int it = 0;
+        for (int p = wg; p < n_pairs && !LS_DBG(8); p += 2, ++it) {
             const int j = NR == 2 ? p >> 1 : p;                      // key tile
-            const int h = NR == 2 ? p & 1 : wg;                      // 64-key half of the tile
-            mbar_wait(bar(B_S_FULL + (p & 1)), (p >> 1) & 1);
+            mbar_wait(bar(B_S_FULL + wg), it & 1);
             if (!warp_valid || LS_DBG(4)) {
                 // padding rows only: keep the barrier protocol, skip the math (their O rows are never read)
-                mbar_arrive(bar(B_P_FULL + (p & 1)));
+                mbar_arrive(bar(B_P_FULL + wg));
                 continue;
             }
             tc_fence_after();
-            if (quad == 0 && lane == 0) LS_TRACE(2, t);
-            const uint32_t buf = lane_addr + COL_SP + bi * 64;
-            uint32_t sv[64];
+            if (quad == 0 && lane == 0) LS_TRACE(2, p);
+            uint32_t sv[128];
             LS_TMEM_LD32(buf, sv);
             LS_TMEM_LD32(buf + 32, (sv + 32));
+            LS_TMEM_LD32(buf + 64, (sv + 64));
+            LS_TMEM_LD32(buf + 96, (sv + 96));
             tmem_wait_ld();
-            if (quad == 0 && lane == 0) LS_TRACE(3, t);
+            if (quad == 0 && lane == 0) LS_TRACE(3, p);
             const int gi = tile_index(j);
             if (gi >= total_tiles) {
-                // per-row visibility word of this half's 64 key slots
+                // per-row visibility words of the tile's 128 key slots
                 const SpecialTile st = sp_tiles[gi - total_tiles];
                 const int rp = rp0 + row;
-                uint64_t vis = 0ull;
+                uint64_t vis0 = 0ull, vis1 = 0ull;
                 if (rp < R) {
                     const int qi = rp / G;
                     if (st.kind == 0) {
                         const int hi = d.causal ? kv_len - (n_q - 1 - qi) : kv_len;      // visible global keys: key < hi
-                        const int cnt = min(max(hi - st.base, 0), st.n_valid) - h * 64;
-                        vis = cnt >= 64 ? ~0ull : (cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull));
+                        const int cnt = min(max(hi - st.base, 0), st.n_valid);
+                        vis0 = cnt >= 64 ? ~0ull : (cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull));
+                        vis1 = cnt >= 128 ? ~0ull : (cnt <= 64 ? 0ull : ((1ull << (cnt - 64)) - 1ull));
                     } else {
                         const uint64_t* w = d.tail_mask + static_cast<size_t>(qi) * LS_MASK_WORDS;
-                        const int k0 = st.base + h * 64;
-                        const int wi = k0 >> 6, sh = k0 & 63;
-                        if (wi < LS_MASK_WORDS) {
-                            vis = w[wi] >> sh;
-                            if (sh && wi + 1 < LS_MASK_WORDS) vis |= w[wi + 1] << (64 - sh);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int k0 = st.base + h * 64;
+                            const int wi = k0 >> 6, sh = k0 & 63;
+                            uint64_t v = 0ull;
+                            if (wi < LS_MASK_WORDS) {
+                                v = w[wi] >> sh;
+                                if (sh && wi + 1 < LS_MASK_WORDS) v |= w[wi + 1] << (64 - sh);
+                            }
+                            const int cnt = st.n_valid - h * 64;
+                            if (cnt < 64) v &= cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull);
+                            if (h == 0) vis0 = v; else vis1 = v;
                         }
-                        const int cnt = st.n_valid - h * 64;
-                        if (cnt < 64) vis &= cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull);
                     }
                 }
 #pragma unroll
-                for (int e = 0; e < 64; ++e)
-                    if (!((vis >> e) & 1ull)) sv[e] = 0xff800000u;                       // -inf
+                for (int e = 0; e < 64; ++e) {
+                    if (!((vis0 >> e) & 1ull)) sv[e] = 0xff800000u;                      // -inf
+                    if (!((vis1 >> e) & 1ull)) sv[64 + e] = 0xff800000u;
+                }
             }
             float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-            for (int e = 0; e < 64; e += 8) {
+            for (int e = 0; e < 128; e += 8) {
                 mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])));
                 mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])));
                 mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sv[e + 4]), __uint_as_float(sv[e + 5])));
@@ -515,12 +598,9 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                 const float alpha = m_ref == -INFINITY ? 0.f : fast_exp2(m_ref - m_new);   // nothing accumulated yet: 0, never exp2(-inf + inf)
                 l *= alpha;
                 m_ref = m_new;
-                if (p >= 1) {
-                    // This accumulator is quiescent once PV(pair p-1) completed, which the commit of iteration p-1 - the
-                    // S_FULL of pair p+1, this warpgroup's next wait anyway - certifies.  That barrier's previous phase
-                    // (pair p-1) completed long ago, so the parity wait cannot alias.
-                    mbar_wait(bar(B_S_FULL + ((p + 1) & 1)), ((p + 1) >> 1) & 1);
-                    tc_fence_after();
+                if (it >= 1) {
+                    // Every earlier PV into this accumulator (pairs p-2, p-4, ...) completed before S_FULL(p) fired
+                    // (the commit that published S(p) was issued after PV(p-2)), so the accumulator is quiescent.
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         uint32_t ov[32];
@@ -531,42 +611,23 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                         LS_TMEM_ST32(o_addr + c * 32, ov);
                     }
                     tmem_wait_st();
-                    tc_fence_before();
                 }
             }
-            // p = 2^(s * c2 - m_ref), packed fp32x2 FMA / ADD
+            // p = 2^(s * c2 - m_ref); P goes back IN PLACE over the first 64 columns of the S tile it came from.
+            // Special tiles keep MUFU for every element: a masked score (-inf) must give exactly 0.
             const float m_use = m_ref == -INFINITY ? 0.f : m_ref;      // row with no visible key so far: p = 2^(-inf) = 0
-            const uint64_t negm = pack2(-m_use, -m_use);
-            uint64_t sum_a = 0ull, sum_b = 0ull;                     // {0.f, 0.f}
-            uint32_t pk[32];
-#pragma unroll
-            for (int e = 0; e < 64; e += 4) {
-                float x0, x1, x2, x3;
-                unpack2(fma2(pack2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), c2x2, negm), x0, x1);
-                unpack2(fma2(pack2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), c2x2, negm), x2, x3);
-                const float p0 = fast_exp2(x0), p1 = fast_exp2(x1), p2 = fast_exp2(x2), p3 = fast_exp2(x3);
-                sum_a = add2(sum_a, pack2(p0, p1));
-                sum_b = add2(sum_b, pack2(p2, p3));
-                pk[e >> 1] = Num<T>::pack(p0, p1);
-                pk[(e >> 1) + 1] = Num<T>::pack(p2, p3);
-            }
-            {
-                float a0, a1;
-                unpack2(add2(sum_a, sum_b), a0, a1);
-                l += a0 + a1;
-            }
-            // P -> in place over the S tile it came from (A operand of the PV MMA, 2 values per 32-bit column)
-            if (quad == 0 && lane == 0) LS_TRACE(4, t);
-            LS_TMEM_ST32(buf, pk);
+            if (gi >= total_tiles) l += exp_phase<T, 0>(sv, buf, c2x2, pack2(-m_use, -m_use));
+            else l += exp_phase<T, LS_TC_POLY>(sv, buf, c2x2, pack2(-m_use, -m_use));
+            if (quad == 0 && lane == 0) LS_TRACE(4, p);
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(bar(B_P_FULL + (p & 1)));
-            if (quad == 0 && lane == 0) LS_TRACE(5, t);
+            mbar_arrive(bar(B_P_FULL + wg));
+            if (quad == 0 && lane == 0) LS_TRACE(5, p);
         }
         // ================= epilogue: normalised partial O + LSE =================
         const int Rtot = d.q_rows * G;
         const int nr_out = min(NRS - rt0, NRL_MAX);                 // row tiles this CTA is responsible for
-        if (n_steps > 0) {
+        if (n_pairs > 0) {
             mbar_wait(bar(B_ALL_DONE), 0);           // single-phase barrier: no parity aliasing
             tc_fence_after();
         }
@@ -581,7 +642,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t ov[32];
-                    if (n_steps > 0) {
+                    if (n_pairs > 0) {
                         LS_TMEM_LD32(o_addr + c * 32, ov);
                         tmem_wait_ld();
                     }
@@ -601,7 +662,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
             }
         } else {
             // One (or no) live row tile: the two warpgroups hold partial states of the SAME rows over alternate key
-            // halves.  Exchange (m, l) through shared memory, then each warpgroup merges and writes 64 of the 128
+            // tiles.  Exchange (m, l) through shared memory, then each warpgroup merges and writes 64 of the 128
             // output columns.  Row tiles without live rows / CTAs without keys write empty partials.
             st_m[wg * 128 + row] = m_ref;
             st_l[wg * 128 + row] = l;
@@ -613,7 +674,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
             const float inv = lt > 0.f ? 1.f / lt : 0.f;
             const float w0 = a0 * inv, w1 = a1 * inv;
             for (int re = 0; re < nr_out; ++re) {
-                const bool live = re == 0 && NR == 1 && n_steps > 0;
+                const bool live = re == 0 && NR == 1 && n_pairs > 0;
                 const int rp = (rt0 + re) * 128 + row;
                 const size_t base = part_base(slot, rp);
                 if (wg == 0 && rp < R) {

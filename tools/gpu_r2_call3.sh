@@ -1,0 +1,8 @@
+#!/bin/bash
+# ncu --set full of the v6 verify-attention kernel (source-level stall samples)
+set -u
+mkdir -p gpurun_out
+( timeout 300 ncu --set full --clock-control none --import-source on -k regex:attn_tc -s 3 -c 1 -o gpurun_out/r2c3_attn_tc_full -f \
+    python tools/prof_attn.py 131072 3 > gpurun_out/r2c3_ncu_full.log 2>&1 )
+tail -5 gpurun_out/r2c3_ncu_full.log
+ls -la gpurun_out/*.ncu-rep
