@@ -47,6 +47,30 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+GOLDEN = os.path.join(ROOT, "tests", "golden", "bench_workload.json")
+
+
+def workload_key():
+    return f"{MODEL}|P={PROMPT}|tree={' '.join(map(str, TREE))}|draft_scale={DRAFT_SCALE}|bf16"
+
+
+def workload_golden():
+    """Facts about the SEEDED synthetic workload measured once on one B200 (tools/make_bench_golden.py) and committed:
+    the target's greedy continuation (vanilla_generate - what any lossless speculative run must emit) and the accepted
+    tokens of every round of the tree-spec generation (the accepted length is a property of the workload at T = 0, not
+    of the implementation, so both bench arms use the same one)."""
+    if os.path.exists(GOLDEN):
+        return json.load(open(GOLDEN)).get(workload_key())
+    return None
+
+
+def golden_tau(W, K, fallback):
+    g = workload_golden()
+    if g and len(g.get("tokens_per_round", [])) >= W + K:
+        return sum(g["tokens_per_round"][W:W + K]) / K, "accepted tokens of rounds [W, W+K) of the seeded workload (tests/golden/bench_workload.json)"
+    return fallback, "published tau (BASELINE.md): no committed record for this workload"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -144,57 +168,68 @@ class CpuSample:
         log(f"[cpu] {ls}-layer round: {dt:.2f} s")
         return dt
 
-    def calibrate(self):
-        # best of two per depth: the first pass through a freshly allocated model pays page faults / thread start-up,
-        # which would otherwise swamp the difference between the 1- and the 2-layer round
-        t1 = min(self.round(1), self.round(1))
-        t2 = min(self.round(2), self.round(2))
-        self.per_layer = max(t2 - t1, 0.0)
-        self.models.pop(2, None)
-        return t1, t2
+    def calibrate(self, deep=3, repeats=3):
+        """Per-layer cost of the verify pass from ALTERNATING 1-layer / `deep`-layer rounds, medians of `repeats`
+        (one untimed pass of each first: freshly allocated models pay page faults and thread start-up).  The wider
+        lever (deep - 1 layers instead of one) and the medians keep the extrapolation stable from run to run."""
+        self.round(1)
+        self.round(deep)
+        t1s, tds = [], []
+        for _ in range(repeats):
+            t1s.append(self.round(1))
+            tds.append(self.round(deep))
+        t1, td = sorted(t1s)[len(t1s) // 2], sorted(tds)[len(tds) // 2]
+        self.per_layer = max(td - t1, 0.0) / (deep - 1)
+        self.models.pop(deep, None)
+        self.t1, self.deep, self.td = t1, deep, td
+        return t1, td
 
     def full_round(self, t1):
         return t1 + (self.full.layers - 1) * self.per_layer
 
 
-def cpu_baseline(tau, threads):
+def _cpu_sample_text(cs, threads):
+    return (f"oracle (CPU port of the reference's PyTorch-eager tree path, fp32, {threads} threads): decode rounds (5 draft steps + "
+            f"tree verify) at {MODEL} widths, {PROMPT}-token context, tree {TREE}, random KV standing in for the prefill, with "
+            f"the target truncated to 1 and {cs.deep} layers (medians of 3 alternating repeats: {cs.t1:.2f} s, {cs.td:.2f} s); "
+            f"full depth = t(1) + {cs.full.layers - 1} x {cs.per_layer:.3f} s per layer")
+
+
+def cpu_baseline(tau, tau_src, threads):
     cs = CpuSample(MODEL, PROMPT, TREE, threads)
-    t1, t2 = cs.calibrate()
+    t1, td = cs.calibrate()
     total = cs.full_round(t1)
     return {"value": tau / total, "unit": UNIT, "cores": threads, "kind": "port",
-            "seconds_per_round": total,
-            "sample": (f"oracle (CPU port of the reference's PyTorch-eager tree path, fp32, {threads} threads): one decode "
-                       f"round at {MODEL} widths, {PROMPT}-token context, tree {TREE}, target truncated to 1 and 2 layers "
-                       f"(best of two each: {t1:.2f} s, {t2:.2f} s) and extrapolated linearly to full depth; random KV stands in "
-                       f"for the prefill; tokens/round = tau of the GPU run ({tau:.2f})")}
+            "seconds_per_round": total, "accepted_len_tau": tau, "tau_source": tau_src,
+            "sample": _cpu_sample_text(cs, threads)}
 
 
 def run_reference(args, rank):
     """--impl reference: the reference algorithm's CPU implementation (oracle port) on all host threads.
-    Each step = one full-width, full-context decode round with a 1-layer target plus (L-1) x the per-layer
-    cost calibrated once in the warm-up (a bounded sample so K steps end within minutes)."""
+    Each step = one MEASURED full-width, full-context decode round with a 1-layer target (the bounded sample);
+    the reported value extrapolates it to full depth with the per-layer cost calibrated in the warm-up."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    tau = float(os.environ.get("LONGSPEC_BENCH_TAU", 3.25))     # BASELINE.md: published tau, Llama-3-8B GovReport
+    W, K = max(args.warmup, 3), args.steps
+    tau, tau_src = golden_tau(W, K, float(os.environ.get("LONGSPEC_BENCH_TAU", 3.25)))
     cs = CpuSample(MODEL, PROMPT, TREE, threads)
-    t1, t2 = cs.calibrate()
-    for _ in range(max(args.warmup - 2, 0)):
-        cs.round(1)
-    per_step = [cs.full_round(cs.round(1)) for _ in range(args.steps)]
-    sec = sum(per_step) / len(per_step)
+    cs.calibrate()                                   # the warm-up: 2 untimed + 6 timed rounds
+    samples = [cs.round(1) for _ in range(K)]
+    med = sorted(samples)[len(samples) // 2]
+    sec = cs.full_round(med)
     val = tau / sec
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+            "warmup": args.warmup, "ms_per_step": sum(samples) / len(samples) * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{MODEL} widths, random-init weights, {PROMPT}-token synthetic context, tree "
                                    f"{' '.join(map(str, TREE))}, bsz 1, T=0",
-                       "note": "CPU: reference algorithm (oracle port of the PyTorch-eager path), all host threads",
-                       "accepted_len_tau": tau},
+                       "note": "CPU: reference algorithm (oracle port of the PyTorch-eager path), all host threads; "
+                               "ms_per_step is the MEASURED bounded sample (a 1-layer round); value = tau / seconds_per_round_full_depth",
+                       "accepted_len_tau": tau, "tau_source": tau_src,
+                       "seconds_per_round_full_depth": sec},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"each step = one decode round (5 draft steps + verify) at full widths and context with a "
-                                       f"1-layer target, plus 31 x the per-layer verify cost calibrated once ({cs.per_layer:.2f} s); "
-                                       f"random KV stands in for the prefill; tokens/round = {tau} (published tau, BASELINE.md)"},
+                             "seconds_per_round": sec, "sample": _cpu_sample_text(cs, threads)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -327,22 +362,46 @@ def main():
                 "tensor_tflops": alg_flops / (attn_ms * 1e-3) / 1e12,
                 "share_of_round": attn_ms * d.layers / (ms / K)}
 
-    if rank != 0:
+    # ---------------- token checks: every rank emitted the same tokens, and they are the target's greedy continuation ----------------
+    n_tok = int(count) + int(num)
+    ranks_agree = None
+    if world > 1:
+        outs = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(outs, out.contiguous())
+        ranks_agree = all(torch.equal(o_, outs[0]) for o_ in outs)
+        assert ranks_agree, "ranks disagree on the generated tokens"
+    gold = workload_golden()
+    tokens_checked, match = 0, None
+    if gold:
+        ref_t = gold["greedy"]
+        tokens_checked = min(n_tok, len(ref_t))
+        match = out_host[0, :tokens_checked].tolist() == ref_t[:tokens_checked]
+        assert match, ("tree-spec output differs from the committed greedy continuation of this seeded workload "
+                       f"(first {tokens_checked} tokens): the run is not lossless")
+
+    def teardown():
+        # captured NCCL kernels must go before the communicator: destroy the graphs, drain the device, then the group
+        nonlocal m, eng, graph, descs
+        m.last_graph = None
+        del graph, descs, eng, m
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-            torch.cuda.synchronize()
-            os._exit(0)                      # skip NCCL / CUDA-graph teardown (can hang with captured collectives)
+            dist.destroy_process_group()
+
+    if rank != 0:
+        teardown()
         return
     # ---------------- (D) CPU baseline beside it (rank 0, N = 1 only) ----------------
+    teardown()
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            del m, eng, graph, descs
             torch.cuda.empty_cache()
-            cpu = cpu_baseline(tau, os.cpu_count() or 1)
+            e2e_tau = e2e_tokens / K
+            cpu = cpu_baseline(e2e_tau, "accepted length of this run's e2e rounds", os.cpu_count() or 1)
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
-    n_tok = int(count) + int(num)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -358,19 +417,21 @@ def main():
                 "ms_per_step": float(e2e_t) * 1e3 / K, "accepted_len_tau": e2e_tokens / K,
                 "note": "LlamaGlide.tree_spec_generate with a pinned host prompt; last K rounds of the call, each with its "
                         "device->host read of the accept/stop counters; prefill excluded like the reference's elapsed_time. "
-                        "These are different rounds of the generation than the replayed ones behind `value`, so the "
-                        "accepted length differs: compare ms_per_step for the host-loop overhead"},
+                        "These are different rounds of the generation than the replayed ones behind `value` (which run later, "
+                        "back to back under the power cap), so the accepted length and the clocks differ: compare ms_per_step "
+                        "for the host-loop overhead"},
         "gpu_launches": int(launches_per_round * K),
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "tokens_checked": n_tok,
+        "tokens_generated": n_tok,
+        "tokens_checked": tokens_checked,
+        "tokens_match_greedy": match,
+        "ranks_agree": ranks_agree,
+        "tokens_check": ("first tokens_checked emitted tokens == the committed greedy (vanilla_generate, 1 GPU) continuation of "
+                         "this seeded workload; ranks_agree = all ranks hold identical output_ids" if gold else
+                         "no committed greedy record for this workload (tools/make_bench_golden.py): unverified"),
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-        sys.stdout.flush()
-        os._exit(0)
 
 
 if __name__ == "__main__":

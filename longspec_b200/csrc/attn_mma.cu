@@ -422,12 +422,10 @@ static int launch_partial_mma(const ls_attn_desc* d, int remainder, void* stream
     const int G = d->n_heads / d->n_kv_heads;
     dim3 grid(d->n_splits, d->n_kv_heads, (d->q_rows * G + kBM - 1) / kBM);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(attn_partial_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        cudaFuncSetAttribute(attn_partial_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        attr_set = true;
-    }
+    static unsigned long long smem_ok_f16 = 0, smem_ok_bf16 = 0;     // one bit per device ordinal
+    rc = d->dtype == LS_F16 ? ensure_dyn_smem(attn_partial_kernel<__half>, kSmemBytes, &smem_ok_f16, "ls_attn_partial")
+                            : ensure_dyn_smem(attn_partial_kernel<__nv_bfloat16>, kSmemBytes, &smem_ok_bf16, "ls_attn_partial");
+    if (rc) return rc;
     if (d->dtype == LS_F16)
         attn_partial_kernel<__half><<<grid, kWarps * 32, kSmemBytes, st>>>(*d, remainder);
     else

@@ -465,6 +465,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
             auto issue_qk = [&]() {
                 if (rq == 0 && !LS_DBG(16)) mbar_wait(bar(B_K_FULL + sq), phq);
                 tc_fence_after();
+                if (lane == 0 && pq >= 2) LS_TRACE(7, pq - 2);
                 if (elect_one()) {
                     const uint32_t a0 = q_lo + rq * (32768 >> 4), b0 = k_lo + sq * (TILE_BYTES >> 4);
                     const uint32_t dst = tmem + COL_SP + (pq & 1) * 128;
@@ -502,6 +503,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                     if (rp == NR - 1) tc_commit(bar(B_V_EMPTY + sp));
                 }
                 __syncwarp();
+                if (lane == 0) LS_TRACE(6, p);
                 if (++rp == NR) {
                     rp = 0;
                     if (++sp == STAGES) { sp = 0; php ^= 1; }
@@ -739,6 +741,10 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
+// A tensor map encodes nothing but (address, extent, dtype): an entry for a freed-and-reallocated pool with the same
+// key is still the right map, so stale entries are harmless; the cache is only bounded so that a long-lived process
+// that keeps allocating pools cannot grow it without limit.
+constexpr size_t MAP_CACHE_MAX = 4096;
 struct MapKey {
     const void* ptr; long long rows; int dtype;
     bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && dtype == o.dtype; }
@@ -765,6 +771,7 @@ static int get_map(const void* pool, long long rows, int dtype, CUtensorMap* out
                      const_cast<void*>(pool), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", static_cast<int>(rc)); return LS_ERR_CUDA; }
+    if (cache.size() >= MAP_CACHE_MAX) cache.clear();
     cache[key] = m;
     *out = m;
     return LS_OK;
@@ -795,12 +802,10 @@ static int launch_tc(const ls_attn_desc* d, int n_splits_tc, int fuse_remainder,
     if (rc) return rc;
     rc = get_map(d->v_pool, rows, d->dtype, &mv);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(attn_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        cudaFuncSetAttribute(attn_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        attr_set = true;
-    }
+    static unsigned long long smem_ok_f16 = 0, smem_ok_bf16 = 0;     // one bit per device ordinal
+    rc = d->dtype == LS_F16 ? ensure_dyn_smem(attn_tc_kernel<__half>, SMEM_BYTES, &smem_ok_f16, "ls_attn_partial_tc")
+                            : ensure_dyn_smem(attn_tc_kernel<__nv_bfloat16>, SMEM_BYTES, &smem_ok_bf16, "ls_attn_partial_tc");
+    if (rc) return rc;
     const int nrs = (d->q_rows * G + 127) / 128;
     dim3 grid(nrs > NRL_MAX ? n_splits_tc + (n_splits_tc + 1) / 2 : n_splits_tc, d->n_kv_heads);
     cudaStream_t st = static_cast<cudaStream_t>(stream);

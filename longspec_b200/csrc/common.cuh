@@ -22,6 +22,23 @@ inline int check_launch(const char* what) {
     return LS_OK;
 }
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute is PER DEVICE, so the "already done"
+// state is a bit per device ordinal (a process may drive several GPUs); a failing call is reported, not ignored.
+template <typename K>
+inline int ensure_dyn_smem(K kernel, int bytes, unsigned long long* done_mask, const char* what) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("%s: cudaGetDevice failed", what); return LS_ERR_CUDA; }
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(done_mask, __ATOMIC_ACQUIRE) & bit) return LS_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+        set_error("%s: cudaFuncSetAttribute(%d bytes of dynamic shared memory) failed: %s", what, bytes, cudaGetErrorString(e));
+        return LS_ERR_CUDA;
+    }
+    __atomic_fetch_or(done_mask, bit, __ATOMIC_RELEASE);
+    return LS_OK;
+}
+
 #define LS_REQUIRE(cond, ...)                 \
     do {                                      \
         if (!(cond)) {                        \

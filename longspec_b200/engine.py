@@ -137,7 +137,8 @@ class Weights:
         self.dims = dims
         cv = lambda t: t.to(device=device, dtype=dtype).contiguous()
         self.embed = cv(sd["model.embed_tokens.weight"])
-        self.lm_head = cv(sd["lm_head.weight"])
+        # checkpoints with tie_word_embeddings ship no lm_head.weight: the head IS the embedding matrix
+        self.lm_head = cv(sd["lm_head.weight"]) if "lm_head.weight" in sd else self.embed
         self.norm = cv(sd["model.norm.weight"])
         self.layers = []
         for i in range(dims.layers):
@@ -171,8 +172,11 @@ class Weights:
         D["ln2"] = cv(sd[g + "post_self_attention_layernorm.weight"])
         D["ln3"] = cv(sd[g + "post_cross_attention_layernorm.weight"])
         self.draft = D
-        inv = 1.0 / (dims.rope_theta ** (torch.arange(0, 128, 2, dtype=torch.int64).float() / 128))
-        self.inv_freq = (inv / dims.rope_factor).to(device)
+        if dims.inv_freq is not None:           # rope types whose frequencies HF computes for us (llama3, ...)
+            self.inv_freq = torch.tensor(dims.inv_freq, dtype=torch.float32, device=device)
+        else:
+            inv = 1.0 / (dims.rope_theta ** (torch.arange(0, 128, 2, dtype=torch.int64).float() / 128))
+            self.inv_freq = (inv / dims.rope_factor).to(device)
 
 
 def alloc_tree_state(dev, tree_shape, prompt_len, max_gen_len):
@@ -503,8 +507,10 @@ class Engine:
         and outside this round's kernel scope.  Fills the paged pools
         (this rank's shard only) and returns the last position's final hidden state [1, hidden]."""
         d, w, sh = self.dims, self.w, self.shard
-        P = input_ids.shape[1]
-        ids = input_ids[0].to(self.device)
+        P = self.prompt_len                      # KV sizing, cache_len and the shard plan were made for prompt_length
+        if input_ids.shape[1] < P:
+            raise ValueError(f"input_ids holds {input_ids.shape[1]} tokens but prompt_length is {P}")
+        ids = input_ids[0, :P].to(self.device)
         pos = torch.arange(P, device=self.device, dtype=torch.int32)
         HD, KD = d.heads * 128, d.kv_heads * 128
         h = w.embed[ids]

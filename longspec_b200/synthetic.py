@@ -34,6 +34,7 @@ class ModelDims:
     qkv_bias: bool = False
     head_dim: int = 128
     max_position_embeddings: int = 1 << 20
+    inv_freq: tuple | None = None        # explicit rotary frequencies [head_dim / 2] (rope types beyond default / linear)
 
     @staticmethod
     def from_hf_config(cfg) -> "ModelDims":
@@ -44,18 +45,30 @@ class ModelDims:
         if theta is None:
             theta = rp.get("rope_theta", 10000.0)
         factor = 1.0
+        inv_freq = None
         rtype = rp.get("rope_type", rp.get("type", "default")) if isinstance(rp, dict) else "default"
         if rtype == "linear":
             factor = float(rp.get("factor", 1.0))
         elif rtype not in ("default", None):
-            raise NotImplementedError(f"rope type {rtype!r} is not supported")
+            # The reference builds its tables with HF's LlamaRotaryEmbedding(config=config) (llama.py:547,585), i.e. with
+            # HF's per-type frequency functions.  The kernels take any STATIC frequency vector, which covers llama3;
+            # types that rescale cos/sin (yarn, longrope) or depend on the sequence length (dynamic) are not supported.
+            if rtype == "dynamic":
+                raise NotImplementedError("rope type 'dynamic' (sequence-length dependent frequencies) is not supported")
+            from transformers.modeling_rope_utils import ROPE_INIT_FUNCTIONS
+            if rtype not in ROPE_INIT_FUNCTIONS:
+                raise NotImplementedError(f"rope type {rtype!r} is not supported")
+            freqs, attention_scaling = ROPE_INIT_FUNCTIONS[rtype](cfg, "cpu")
+            if abs(float(attention_scaling) - 1.0) > 1e-6:
+                raise NotImplementedError(f"rope type {rtype!r} rescales cos/sin by {attention_scaling}: not supported")
+            inv_freq = tuple(float(x) for x in freqs.float().tolist())
         hd = getattr(cfg, "head_dim", None) or cfg.hidden_size // cfg.num_attention_heads
         bias = bool(getattr(cfg, "attention_bias", False)) or cfg.__class__.__name__.startswith("Qwen2")
         return ModelDims(hidden=cfg.hidden_size, heads=cfg.num_attention_heads,
                          kv_heads=cfg.num_key_value_heads, layers=cfg.num_hidden_layers,
                          ffn=cfg.intermediate_size, vocab=cfg.vocab_size, rope_theta=float(theta),
                          rope_factor=factor, rms_eps=cfg.rms_norm_eps, qkv_bias=bias, head_dim=hd,
-                         max_position_embeddings=cfg.max_position_embeddings)
+                         max_position_embeddings=cfg.max_position_embeddings, inv_freq=inv_freq)
 
 
 # Architecture dims of BASELINE.json's configs (SURVEY.md section 8 header).
@@ -71,6 +84,10 @@ PRESETS = {
     "tiny": ModelDims(256, 2, 1, 2, 512, 320),
     "tiny-gqa": ModelDims(512, 4, 2, 3, 768, 512),
     "tiny-qwen": ModelDims(256, 2, 1, 2, 512, 320, qkv_bias=True, rope_theta=1e6),
+    # the headline head geometry (GQA-4: 74 verify tokens -> 296 packed rows -> heavy/heavy/light CTA trios) at toy widths
+    "tiny-g4": ModelDims(1024, 8, 2, 2, 1024, 512),
+    # MHA at toy widths (Vicuna-like: one head per kv head, wide trees make two row tiles)
+    "tiny-mha": ModelDims(512, 4, 4, 2, 768, 512, rope_factor=4.0),
 }
 
 

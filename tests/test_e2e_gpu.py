@@ -101,3 +101,80 @@ def test_eos_stops_like_the_reference():
     assert out2[0, :n2].tolist() == toks[:n2]
     first = toks.index(eos)
     assert n2 >= first + 1 and n2 <= first + 1 + 3, "stops at the end of the round that produced eos"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CUDA path vs the oracle run on this box's CPU (no committed fixture: the oracle is pinned to the reference by
+# tests/test_oracle_golden.py).  These cases cover what the fixtures cannot: prompts long enough for the draft-cache
+# tail shortcut (engine.py: first_needed = P - 512 - 256 only engages for P > 768), the headline head geometry
+# (8 heads / 2 kv heads: 296 packed verify rows = heavy/heavy/light CTA trios inside the loop) and the wide tree.
+# ---------------------------------------------------------------------------------------------------------------
+def _oracle_tokens(dims, W, ids, P, shape, gen_len, eos):
+    from oracle.generate import tree_spec_generate as oracle_tree
+    from oracle.model import Dims, OracleModel
+    om = OracleModel(Dims(**{k: getattr(dims, k) for k in Dims.__dataclass_fields__}), W)
+    ref, rc, rn, _, _ = oracle_tree(om, ids, P, tree_shape=shape, max_gen_len=gen_len, eos_id=eos)
+    return ref, rc, rn
+
+
+ORACLE_CASES = [
+    # preset, prompt length, tree, max_gen_len, dtype, draft_scale
+    ("tiny-gqa", 1500, [4, 16, 16, 16, 16], 40, torch.bfloat16, None),
+    ("tiny-gqa", 4000, [4, 16, 16, 16, 16], 40, torch.float16, 2.0),
+    ("tiny-g4", 1500, [4, 16, 16, 16, 16], 40, torch.bfloat16, None),
+    ("tiny-g4", 900, [4, 16, 16, 16, 16], 48, torch.float16, 2.0),
+    ("tiny-gqa", 1500, [8, 32, 32, 32, 32], 56, torch.bfloat16, None),
+    ("tiny-mha", 1500, [8, 32, 32, 32, 32], 56, torch.float16, None),
+    ("tiny-g4", 1300, [8, 32, 32, 32, 32], 56, torch.bfloat16, None),
+]
+
+
+@pytest.mark.parametrize("preset,P,shape,gen_len,dtype,ds", ORACLE_CASES)
+def test_tree_tokens_match_oracle_long_prompt_and_headline_geometry(preset, P, shape, gen_len, dtype, ds):
+    from longspec_b200.llama_glide import LlamaGlide
+    from longspec_b200.synthetic import synthetic_prompt
+    dims = PRESETS[preset]
+    W = synthetic_state_dict(dims, seed=11, draft_scale=ds)
+    ids = synthetic_prompt(dims.vocab, P, seed=11)
+    eos = dims.vocab + 9
+    m = LlamaGlide(dims, W, None, dtype=dtype, shuffle_pages=True)
+    out, count, num, _, _ = m.tree_spec_generate(ids.cuda(), torch.tensor([P]).cuda(), tree_shape=shape,
+                                                 max_gen_len=gen_len, eos_id=eos)
+    if P > 768:
+        assert m.eng.draft_first > 0, "the draft-cache tail shortcut must be engaged in this test"
+    ref, rc, rn = _oracle_tokens(dims, W, ids, P, shape, gen_len, eos)
+    got = out[0].cpu().numpy()
+    n_ref = rc + rn
+    assert np.array_equal(got[:n_ref], ref[:n_ref]), f"CUDA tree path != oracle ({preset}, P={P}, {shape}, {dtype})\n{got}\n{ref}"
+    if ds is None:
+        assert (int(count), num) == (rc, rn), "same rounds and accepted counts as the oracle"
+        assert np.array_equal(got, ref)
+
+
+def test_right_padded_input_ids_are_sliced_to_prompt_length():
+    """The reference reads hidden_states[:, input_len - 1] (llama_glide.py:955): tokens behind prompt_length are padding."""
+    from longspec_b200.llama_glide import LlamaGlide
+    from longspec_b200.synthetic import synthetic_prompt
+    dims = PRESETS["tiny"]
+    W = synthetic_state_dict(dims, seed=2)
+    ids = synthetic_prompt(dims.vocab, 300, seed=2)
+    m = LlamaGlide(dims, W, None, dtype=torch.float16)
+    kw = dict(tree_shape=[4, 4], max_gen_len=24, eos_id=dims.vocab + 3)
+    a = m.tree_spec_generate(ids[:, :200].cuda(), torch.tensor([200]).cuda(), **kw)
+    b = m.tree_spec_generate(ids.cuda(), torch.tensor([200]).cuda(), **kw)
+    assert torch.equal(a[0], b[0]) and int(a[1]) == int(b[1]) and a[2] == b[2]
+
+
+def test_sequence_sharded_generation_on_two_gpus_matches_single_gpu():
+    """2-rank NCCL run (skipped on a 1-GPU box): prefix KV sharded over two GPUs, headline head geometry, prompt long
+    enough for the draft tail shortcut; tools/check_multigpu.py asserts rank equality and equality with the 1-GPU run."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "tools", "check_multigpu.py"), "tiny-g4", "3000"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "multi-GPU check ok" in res.stdout

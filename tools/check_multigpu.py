@@ -33,7 +33,10 @@ if rank == 0:
     assert torch.equal(ref, out), f"sharded != single GPU\n{ref}\n{out}"
     assert (int(c1), n1) == (int(count), num)
     print(f"multi-GPU check ok: world={world}, {int(count) + num} tokens identical to the single-GPU run", flush=True)
-dist.barrier()
+# teardown in dependency order: the captured graphs (they hold NCCL kernels) before the communicator
+m.last_graph = None
+m.eng = None
+del m
 torch.cuda.synchronize()
-sys.stdout.flush()
-os._exit(0)      # skip NCCL/graph teardown (can hang with captured collectives)
+dist.barrier()
+dist.destroy_process_group()

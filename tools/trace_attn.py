@@ -2,7 +2,7 @@
    python tools/trace_attn.py build          (here: cross-compiles tools/ubench/liblongspec_trace.so)
    python tools/trace_attn.py [N=131072]     (on the GPU box)
 Events per step t: 0 MMA warp saw P_FULL(t) | 1 MMA warp issued PV(t)+QK(t+2) | 2 softmax saw S_FULL(t) |
-3 S loaded | 4 exp done | 5 P stored + arrived."""
+3 S loaded | 4 exp done | 5 P stored + arrived | 6 PV(t) issued | 7 K tile of QK(t+2) seen ready."""
 import os
 import subprocess
 import sys
@@ -50,6 +50,10 @@ print(f"MMA warp (per PAIR of steps, {valid} pairs traced):")
 print("  mean pair period            :", float(np.diff(e[0, sl]).mean()))
 print("  P_FULL seen -> pair issued  :", float((e[1, sl] - e[0, sl]).mean()))
 print("  issued -> next P_FULL seen  :", float((e[0, sl.start + 1:sl.stop + 1] - e[1, sl]).mean()))
+if int((e[6] != 0).sum()) > 30:
+    print("  P_FULL seen -> PV issued    :", float((e[6, sl] - e[0, sl]).mean()))
+    print("  PV issued -> K tile ready   :", float((e[7, sl] - e[6, sl]).mean()))
+    print("  K tile ready -> QK issued   :", float((e[1, sl] - e[7, sl]).mean()))
 vs = int((e[2] != 0).sum())
 ss = slice(40, max(vs - 20, 42))
 if vs > 60:
