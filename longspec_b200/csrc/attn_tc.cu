@@ -6,10 +6,12 @@
 // TMEM (512 columns) = two 128-column S/P buffers + two 128-column O accumulators - the FA4 shape.  A PAIR is
 // (key tile, row tile): ONE S = Q K^T with N = 128 keys (tensor-rate; the N = 64 form of round 1 was bound by
 // shared-memory operand bandwidth), one softmax pass, ONE O += P V with K = 128 keys.  Pair p lives in S/P buffer
-// p & 1, accumulates into O accumulator p & 1, and belongs to softmax warpgroup p & 1, which keeps the (m, l) row
-// state in REGISTERS and never shares it.  Two row tiles: pair p = (key tile p >> 1, row tile p & 1), i.e. one
-// warpgroup + accumulator per row tile.  One row tile: pair p = key tile p, the warpgroups take alternate key
-// tiles into two accumulators and the epilogue merges the two partial states.
+// p & 1 and accumulates into O accumulator p & 1.  FOUR softmax warpgroups: buffer b belongs to warpgroups 2b and
+// 2b + 1, which take the two 64-key halves of every pair in that buffer (a single warpgroup per pair is latency-bound:
+// 1390 cycles per 128 x 128 tile against 1030 of MMA - profiles/r02_*; four warps per scheduler hide it).  The two
+// threads of a row share its reference maximum - identical in both by construction - and keep private partial sums.
+// Two row tiles: pair p = (key tile p >> 1, row tile p & 1), i.e. one accumulator per row tile.  One row tile: pair
+// p = key tile p, alternate key tiles go to the two accumulators and the epilogue merges the two partial states.
 // A call with three row tiles (the Llama-3 verify shape: 74 tokens x GQA-4 = 296 rows) is cut into "trios": two
 // HEAVY CTAs (row tiles 0-1, alternate key tiles of the group's range) and one LIGHT CTA (row tile 2, every key
 // tile of the range).  All three run the same number of pairs, and the light CTA's K/V loads hit L2 behind the
@@ -23,10 +25,11 @@
 //                       MMAs of one thread execute in issue order, so QK(p+2) cannot overwrite the buffer PV(p)
 //                       still reads: no "buffer free" barriers, one wait and one commit per 16 MMAs.
 //   warp 2              TMEM allocation
-//   warps 4-7 / 8-11    two softmax warpgroups (setmaxnreg 216; warps 0-3 drop to 72).  One row per thread:
-//                       tcgen05.ld the 128-key S tile, online softmax in the log2 domain with lazy rescaling (O in
-//                       TMEM is only rescaled when a row maximum grows by more than 2^8), P rounded to dtype and
-//                       tcgen05.st IN PLACE over the first 64 columns of the S buffer it came from.  The kernel sits
+//   warps 4-19          four softmax warpgroups (setmaxnreg 112; warps 0-3 drop to 32).  Half a row per thread:
+//                       tcgen05.ld 64 keys of the S tile, online softmax in the log2 domain with lazy rescaling (O in
+//                       TMEM is only rescaled when a row maximum grows by more than 2^8; one bar.red.or over the 64
+//                       threads that share a TMEM lane quarter and a buffer decides it), P rounded to dtype and
+//                       tcgen05.st IN PLACE over the first 32 columns of the S half it came from.  The kernel sits
 //                       where MUFU (16 ex2/clk/SM) and the tensor pipe cost the same per tile, so LS_TC_POLY of
 //                       every 8 exponentials are computed on the FMA pipe instead (Cody-Waite + cubic, rel. error
 //                       2^-13.2 - below the rounding of P to bf16/fp16; tools/ubench/softmax_math.cu).
@@ -54,10 +57,10 @@ constexpr int BN = 128;                            // keys per tile
 constexpr int NRL_MAX = 2;                         // row tiles per CTA
 constexpr int NR_MAX = 3;                          // row tiles per call
 constexpr int STAGES = 2;                          // K ring and V ring depth
-constexpr int THREADS = 384;
+constexpr int THREADS = 640;                       // 4 control warps + 16 softmax warps
 constexpr int TILE_BYTES = 32768;                  // one K or V tile: [2 x 64-element chunks][128 keys][128 B]
 constexpr int Q_BYTES = NRL_MAX * 32768;           // [row tile][2 k-chunks][128 rows][128 B]
-constexpr int STATE_BYTES = 2 * 2 * 128 * 4;       // epilogue exchange of (m_ref, l) between the warpgroups
+constexpr int STATE_BYTES = 4096;                  // row-maximum exchange between the two halves of a row / epilogue exchange
 constexpr int BAR_BYTES = 256;
 constexpr int SPECIAL_BYTES = 256;                 // special-tile table (12 x 16 B)
 constexpr int OFF_K = Q_BYTES;
@@ -72,6 +75,8 @@ constexpr uint32_t COL_SP = 0;                     // two buffers of 128 columns
                                                    // in place by its 128 x 128 bf16/fp16 probability tile (64 columns)
 constexpr uint32_t COL_O = 256;                    // 2 x 128
 
+constexpr int BAR_Q_READY = 15;                    // named barrier: Q staged (softmax warps arrive, the MMA issuer waits)
+constexpr int OUT_STRIDE = 132;                    // floats per staged output row (128 + 4: conflict-free 16-byte stores)
 constexpr int MAX_SPECIAL = 12;
 struct SpecialTile {
     int tok;      // first LOCAL token of the tile (need not be 128-aligned for tail tiles)
@@ -214,10 +219,12 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 
 // Optional event trace of CTA (0, 0) for tools/trace_attn.py (compiled in only with -DLS_TC_TRACE)
 #ifdef LS_TC_TRACE
-__device__ int g_dbg = 0;     // timing experiments (results become wrong): 1 no PV MMAs, 2 no QK MMAs, 4 no softmax math
+__device__ int g_dbg = 0;     // timing experiments (results become wrong): 1 no PV MMAs, 2 no QK MMAs, 4 no softmax math, 16 no TMA;
+                              // bits 16.. = blockIdx.x of the traced CTA
 #define LS_DBG(bit) (dbg & (bit))
 __device__ long long* g_trace = nullptr;
-#define LS_TRACE_INIT long long* const trace_buf = (blockIdx.x == 0 && blockIdx.y == 0) ? g_trace : nullptr; const int dbg = g_dbg;
+#define LS_TRACE_INIT const int dbg = g_dbg & 0xffff; long long* const trace_buf = (static_cast<int>(blockIdx.x) == (g_dbg >> 16) && blockIdx.y == 0) ? g_trace : nullptr; \
+    if (trace_buf && threadIdx.x == 0) trace_buf[7 * 512 + 511] = clock64();   /* kernel entry of the traced CTA */
 #define LS_TRACE(ev, t)                                                       \
     do {                                                                      \
         if (trace_buf && (t) < 512) trace_buf[(ev) * 512 + (t)] = clock64();  \
@@ -237,14 +244,20 @@ __device__ long long* g_trace = nullptr;
                    "r"(v[15])                                                                                         \
                  : "memory")
 
+#define LS_TMEM_LD16(taddr, v)                                                                                       \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),     \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) \
+                 : "r"(taddr))
+
 // Register budget (setmaxnreg works per warpgroup): warps 0-3 (TMA, MMA issue, TMEM allocation) give registers back,
-// the two softmax warpgroups hold a whole 128-key score row per thread.  setmaxnreg only moves registers inside the
-// pool the CTA was LAUNCHED with (384 threads x 168 registers = 64512, not the SM's 65536): a request beyond it blocks
-// forever, so 128 * REGS_CTRL + 256 * REGS_SOFTMAX must not exceed THREADS * 168.
-constexpr int REGS_LAUNCH = 168;                   // __launch_bounds__(384, 1)
-constexpr int REGS_CTRL = 72;
-constexpr int REGS_SOFTMAX = 216;
-static_assert(128 * REGS_CTRL + 256 * REGS_SOFTMAX <= THREADS * REGS_LAUNCH, "setmaxnreg budget exceeds the CTA's register pool");
+// the four softmax warpgroups hold 64 scores per thread.  setmaxnreg only moves registers inside the pool the CTA was
+// LAUNCHED with (640 threads x 96 registers = 61440, not the SM's 65536): a request beyond it blocks forever, so
+// 128 * REGS_CTRL + 512 * REGS_SOFTMAX must not exceed THREADS * REGS_LAUNCH.
+constexpr int REGS_LAUNCH = 96;                    // __launch_bounds__(640, 1): floor(65536 / 640) rounded down to 8
+constexpr int REGS_CTRL = 32;
+constexpr int REGS_SOFTMAX = 112;
+static_assert(128 * REGS_CTRL + 512 * REGS_SOFTMAX <= THREADS * REGS_LAUNCH, "setmaxnreg budget exceeds the CTA's register pool");
 static_assert(REGS_CTRL % 8 == 0 && REGS_SOFTMAX % 8 == 0, "setmaxnreg takes multiples of 8");
 template <int N>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -282,14 +295,14 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
     p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
 }
 
-// The exponential phase of one 128-key score row: p = 2^(s * c2 - m), packed fp32x2 FMA / ADD, POLY of every 8
+// The exponential phase of half a score row (64 keys): p = 2^(s * c2 - m), packed fp32x2 FMA / ADD, POLY of every 8
 // exponentials on the FMA pipe and the rest on MUFU; P is rounded to the 16-bit type and stored to TMEM (A operand of
 // the PV MMA, 2 values per 32-bit column) one 32-key slice at a time.  Returns the row sum of the unrounded p.
 template <typename T, int POLY>
-__device__ __forceinline__ float exp_phase(const uint32_t (&sv)[128], uint32_t buf, uint64_t c2x2, uint64_t negm) {
+__device__ __forceinline__ float exp_phase(const uint32_t (&sv)[64], uint32_t buf, uint64_t c2x2, uint64_t negm) {
     uint64_t sum_a = 0ull, sum_b = 0ull;                     // {0.f, 0.f}
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
@@ -375,8 +388,6 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
     const int n_pairs = n_tiles * NR;
     auto tile_index = [&](int j) { return tile_lo + j * stride; };   // position in the call's tile sequence
 
-    float* st_m = reinterpret_cast<float*>(smem + OFF_STATE);        // epilogue exchange only (one row tile)
-    float* st_l = st_m + 2 * 128;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + B_COUNT * 8);
     const uint32_t bar0 = sbase + OFF_BAR;
     auto bar = [&](int i) { return bar0 + i * 8; };
@@ -387,7 +398,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
             mbar_init(bar(B_K_FULL + i), 1); mbar_init(bar(B_K_EMPTY + i), 1);
             mbar_init(bar(B_V_FULL + i), 1); mbar_init(bar(B_V_EMPTY + i), 1);
         }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar(B_S_FULL + i), 1); mbar_init(bar(B_P_FULL + i), 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar(B_S_FULL + i), 1); mbar_init(bar(B_P_FULL + i), 256); }
         mbar_init(bar(B_ALL_DONE), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -395,28 +406,13 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    // Q tiles -> swizzled shared memory (K-major, SWIZZLE_128B): [tile][k-chunk][row][128B]
-    if (n_pairs > 0) {
-        const T* __restrict__ q = reinterpret_cast<const T*>(d.q);
-        const size_t q_stride = d.q_stride > 0 ? static_cast<size_t>(d.q_stride) : static_cast<size_t>(d.n_heads) * 128;
-        for (int idx = tid; idx < NR * 128 * 16; idx += THREADS) {
-            const int rl = idx >> 4, chunk = idx & 15;
-            const int tile = rl >> 7, row = rl & 127;
-            const int rp = rt0 * 128 + rl;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (rp < R) {
-                const int i = rp / G, g = rp - i * G;
-                val = *reinterpret_cast<const uint4*>(q + static_cast<size_t>(i) * q_stride + static_cast<size_t>(kvh * G + g) * 128 + chunk * 8);
-            }
-            uint8_t* dst = smem + tile * 32768 + (chunk >> 3) * 16384 + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
-            *reinterpret_cast<uint4*>(dst) = val;
-        }
-    }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // Q is staged by the sixteen softmax warps while the TMA producer already streams the first K/V tiles; only the
+    // MMA issuer waits for it (named barrier B_Q_READY: 512 arrivals + the issuer warp).
 
     constexpr int FMT = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
     constexpr uint32_t IDESC_QK = make_idesc(128, 128, FMT, 0, 0);
@@ -460,6 +456,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
             const uint32_t q_lo = (sbase >> 4) | LBO_K;
             const uint32_t k_lo = ((sbase + OFF_K) >> 4) | LBO_K;
             const uint32_t v_lo = ((sbase + OFF_V) >> 4) | LBO_V;
+            asm volatile("bar.sync %0, %1;" ::"n"(BAR_Q_READY), "n"(512 + 32) : "memory");     // Q tiles are in shared memory
             int pq = 0, rq = 0, sq = 0, phq = 0;          // next QK pair: index, row tile, K stage, K_FULL parity
             int rp = 0, sp = 0, php = 0;                  // next PV pair: row tile, V stage, V_FULL parity
             auto issue_qk = [&]() {
@@ -498,8 +495,9 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                     const uint32_t dst = tmem + COL_O + (p & 1) * 128;
                     if (!LS_DBG(1))
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)      // 16 keys = 8 packed TMEM columns per K step
-                        tc_mma_ts(dst, a0 + kk * 8, b0 + kk * (2048 >> 4), IDESC_PV, (p >= 2 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < 8; ++kk)      // 16 keys = 8 packed TMEM columns per K step; P of keys 0-63 sits in
+                                                        // columns 0-31 of the buffer, P of keys 64-127 in columns 64-95
+                        tc_mma_ts(dst, a0 + (kk >> 2) * 64 + (kk & 3) * 8, b0 + kk * (2048 >> 4), IDESC_PV, (p >= 2 || kk > 0) ? 1u : 0u);
                     if (rp == NR - 1) tc_commit(bar(B_V_EMPTY + sp));
                 }
                 __syncwarp();
@@ -518,113 +516,157 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         }
     } else {
         reg_inc<REGS_SOFTMAX>();
+        // Q tiles -> swizzled shared memory (K-major, SWIZZLE_128B): [tile][k-chunk][row][128B].  All loads of a thread are
+        // issued before its first store (4 x 16 B per row tile and thread), so the staging costs one memory round trip.
+        {
+            const T* __restrict__ q = reinterpret_cast<const T*>(d.q);
+            const size_t q_stride = d.q_stride > 0 ? static_cast<size_t>(d.q_stride) : static_cast<size_t>(d.n_heads) * 128;
+            const int stid = tid - 128;
+            uint4 qv[NRL_MAX * 4];
+#pragma unroll
+            for (int k = 0; k < NRL_MAX * 4; ++k) {
+                const int idx = stid + k * 512;
+                const int rl = idx >> 4, chunk = idx & 15;
+                const int rp = rt0 * 128 + rl;
+                qv[k] = make_uint4(0, 0, 0, 0);
+                if (k < NR * 4 && n_pairs > 0 && rp < R) {
+                    const int i = rp / G, g = rp - i * G;
+                    qv[k] = *reinterpret_cast<const uint4*>(q + static_cast<size_t>(i) * q_stride + static_cast<size_t>(kvh * G + g) * 128 + chunk * 8);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NRL_MAX * 4; ++k) {
+                const int idx = stid + k * 512;
+                const int rl = idx >> 4, chunk = idx & 15;
+                const int tile = rl >> 7, row = rl & 127;
+                if (k < NR * 4 && n_pairs > 0)
+                    *reinterpret_cast<uint4*>(smem + tile * 32768 + (chunk >> 3) * 16384 + row * 128 + (((chunk & 7) ^ (row & 7)) << 4)) = qv[k];
+            }
+            fence_async_smem();                                      // generic-proxy writes -> visible to the MMA's async-proxy reads
+            asm volatile("bar.arrive %0, %1;" ::"n"(BAR_Q_READY), "n"(512 + 32) : "memory");
+        }
         // ================= softmax warpgroups =================
-        const int wg = (warp - 4) >> 2;                              // = pair parity = S/P buffer = O accumulator
+        // Warpgroup wgi = 2 * b + h: 64-key half h of every pair in buffer b (= accumulator b).  The two threads (h = 0, 1)
+        // of a row share the row's reference maximum m_ref - identical in both by construction - and keep private
+        // partial sums l.  The lazy rescale needs both halves' maxima: one bar.red.or over the 64 threads of the two
+        // warps that share (buffer, TMEM lane quarter) tells both whether ANY of their rows has to move its reference;
+        // only then do they exchange maxima through shared memory and rescale the accumulator (each thread 64 of its
+        // row's 128 columns).
+        const int wgi = (warp - 4) >> 2;
+        const int b = wgi >> 1, h = wgi & 1;
         const int quad = warp & 3;                                   // TMEM lane quarter of this warp
         const int row = quad * 32 + lane;                            // row inside a 128-row tile
         const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16);
         const float c2 = d.scale * 1.4426950408889634f;
         const uint64_t c2x2 = pack2(c2, c2);
-        const int rl = NR == 2 ? wg : 0;                             // local row tile of this warpgroup
+        const int rl = NR == 2 ? b : 0;                              // local row tile of this buffer
         const int rp0 = (rt0 + rl) * 128;                            // its first packed row
-        const bool warp_valid = rp0 + quad * 32 < R;                 // warp-uniform: any live row in this warp
-        const uint32_t o_addr = lane_addr + COL_O + wg * 128;
-        const uint32_t buf = lane_addr + COL_SP + wg * 128;
-        float m_ref = -INFINITY, l = 0.f;                            // this thread's row, this warpgroup's pairs
+        const bool warp_valid = rp0 + quad * 32 < R;                 // warp-uniform, the same in both warps of a pair
+        const uint32_t o_half = lane_addr + COL_O + b * 128 + h * 64;
+        const uint32_t buf = lane_addr + COL_SP + b * 128 + h * 64;  // this thread's 64 score columns; P goes to the first 32
+        const int pair_bar = 2 + b * 4 + quad;                       // named barrier of the two warps sharing (b, quad)
+        float* xch = reinterpret_cast<float*>(smem + OFF_STATE);     // [2 buffers][2 halves][128 rows]
+        float m_ref = -INFINITY, l = 0.f;                            // this thread's row (shared m_ref), its own key half
         int it = 0;
-        for (int p = wg; p < n_pairs && !LS_DBG(8); p += 2, ++it) {
+        for (int p = b; p < n_pairs && !LS_DBG(8); p += 2, ++it) {
             const int j = NR == 2 ? p >> 1 : p;                      // key tile
-            mbar_wait(bar(B_S_FULL + wg), it & 1);
+            mbar_wait(bar(B_S_FULL + b), it & 1);
             if (!warp_valid || LS_DBG(4)) {
                 // padding rows only: keep the barrier protocol, skip the math (their O rows are never read)
-                mbar_arrive(bar(B_P_FULL + wg));
+                mbar_arrive(bar(B_P_FULL + b));
                 continue;
             }
             tc_fence_after();
-            if (quad == 0 && lane == 0) LS_TRACE(2, p);
-            uint32_t sv[128];
+            if (quad == 0 && lane == 0 && h == 0) LS_TRACE(2, p);
+            uint32_t sv[64];
             LS_TMEM_LD32(buf, sv);
             LS_TMEM_LD32(buf + 32, (sv + 32));
-            LS_TMEM_LD32(buf + 64, (sv + 64));
-            LS_TMEM_LD32(buf + 96, (sv + 96));
             tmem_wait_ld();
-            if (quad == 0 && lane == 0) LS_TRACE(3, p);
+            if (quad == 0 && lane == 0 && h == 0) LS_TRACE(3, p);
             const int gi = tile_index(j);
             if (gi >= total_tiles) {
-                // per-row visibility words of the tile's 128 key slots
+                // per-row visibility word of this half's 64 key slots
                 const SpecialTile st = sp_tiles[gi - total_tiles];
                 const int rp = rp0 + row;
-                uint64_t vis0 = 0ull, vis1 = 0ull;
+                uint64_t vis = 0ull;
                 if (rp < R) {
                     const int qi = rp / G;
                     if (st.kind == 0) {
                         const int hi = d.causal ? kv_len - (n_q - 1 - qi) : kv_len;      // visible global keys: key < hi
-                        const int cnt = min(max(hi - st.base, 0), st.n_valid);
-                        vis0 = cnt >= 64 ? ~0ull : (cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull));
-                        vis1 = cnt >= 128 ? ~0ull : (cnt <= 64 ? 0ull : ((1ull << (cnt - 64)) - 1ull));
+                        const int cnt = min(max(hi - st.base, 0), st.n_valid) - h * 64;
+                        vis = cnt >= 64 ? ~0ull : (cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull));
                     } else {
                         const uint64_t* w = d.tail_mask + static_cast<size_t>(qi) * LS_MASK_WORDS;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int k0 = st.base + h * 64;
-                            const int wi = k0 >> 6, sh = k0 & 63;
-                            uint64_t v = 0ull;
-                            if (wi < LS_MASK_WORDS) {
-                                v = w[wi] >> sh;
-                                if (sh && wi + 1 < LS_MASK_WORDS) v |= w[wi + 1] << (64 - sh);
-                            }
-                            const int cnt = st.n_valid - h * 64;
-                            if (cnt < 64) v &= cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull);
-                            if (h == 0) vis0 = v; else vis1 = v;
+                        const int k0 = st.base + h * 64;
+                        const int wi = k0 >> 6, sh = k0 & 63;
+                        if (wi < LS_MASK_WORDS) {
+                            vis = w[wi] >> sh;
+                            if (sh && wi + 1 < LS_MASK_WORDS) vis |= w[wi + 1] << (64 - sh);
                         }
+                        const int cnt = st.n_valid - h * 64;
+                        if (cnt < 64) vis &= cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull);
                     }
                 }
 #pragma unroll
-                for (int e = 0; e < 64; ++e) {
-                    if (!((vis0 >> e) & 1ull)) sv[e] = 0xff800000u;                      // -inf
-                    if (!((vis1 >> e) & 1ull)) sv[64 + e] = 0xff800000u;
-                }
+                for (int e = 0; e < 64; ++e)
+                    if (!((vis >> e) & 1ull)) sv[e] = 0xff800000u;                       // -inf
             }
             float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-            for (int e = 0; e < 128; e += 8) {
+            for (int e = 0; e < 64; e += 8) {
                 mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])));
                 mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])));
                 mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sv[e + 4]), __uint_as_float(sv[e + 5])));
                 mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sv[e + 6]), __uint_as_float(sv[e + 7])));
             }
             const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c2;
-            const bool need = mx > m_ref + 8.0f;                     // lazy rescale threshold (2^8)
-            if (__any_sync(0xffffffffu, need)) {
-                const float m_new = need ? mx : m_ref;
-                const float alpha = m_ref == -INFINITY ? 0.f : fast_exp2(m_ref - m_new);   // nothing accumulated yet: 0, never exp2(-inf + inf)
+            // does ANY row of this (buffer, lane quarter) - either half - have to move its reference?
+            uint32_t any;
+            {
+                const uint32_t need = mx > m_ref + 8.0f ? 1u : 0u;   // lazy rescale threshold (2^8)
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred pin, pout;\n\t"
+                    "setp.ne.u32 pin, %1, 0;\n\t"
+                    "bar.red.or.pred pout, %2, 64, pin;\n\t"
+                    "selp.u32 %0, 1, 0, pout;\n\t"
+                    "}" : "=r"(any) : "r"(need), "r"(pair_bar) : "memory");
+            }
+            if (any) {
+                xch[(b * 2 + h) * 128 + row] = mx;
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                const float joint = fmaxf(mx, xch[(b * 2 + (h ^ 1)) * 128 + row]);
+                const float m_new = joint > m_ref + 8.0f ? joint : m_ref;   // the same decision in both threads of the row
+                const float alpha = m_ref == -INFINITY ? 0.f : fast_exp2(m_ref - m_new);   // nothing accumulated yet: 0 (never exp2(-inf + inf)); 1 if unchanged
                 l *= alpha;
                 m_ref = m_new;
                 if (it >= 1) {
                     // Every earlier PV into this accumulator (pairs p-2, p-4, ...) completed before S_FULL(p) fired
                     // (the commit that published S(p) was issued after PV(p-2)), so the accumulator is quiescent.
-#pragma unroll
+                    // (16 columns at a time: the 64 scores of this pair stay live in registers meanwhile)
+#pragma unroll 1
                     for (int c = 0; c < 4; ++c) {
-                        uint32_t ov[32];
-                        LS_TMEM_LD32(o_addr + c * 32, ov);
+                        uint32_t ov[16];
+                        LS_TMEM_LD16(o_half + c * 16, ov);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
-                        LS_TMEM_ST32(o_addr + c * 32, ov);
+                        for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+                        LS_TMEM_ST16(o_half + c * 16, ov);
                     }
                     tmem_wait_st();
                 }
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // xch is reused by the next exchange
             }
-            // p = 2^(s * c2 - m_ref); P goes back IN PLACE over the first 64 columns of the S tile it came from.
+            // p = 2^(s * c2 - m_ref); P goes back IN PLACE over the first 32 columns of the S half it came from.
             // Special tiles keep MUFU for every element: a masked score (-inf) must give exactly 0.
             const float m_use = m_ref == -INFINITY ? 0.f : m_ref;      // row with no visible key so far: p = 2^(-inf) = 0
             if (gi >= total_tiles) l += exp_phase<T, 0>(sv, buf, c2x2, pack2(-m_use, -m_use));
             else l += exp_phase<T, LS_TC_POLY>(sv, buf, c2x2, pack2(-m_use, -m_use));
-            if (quad == 0 && lane == 0) LS_TRACE(4, p);
+            if (quad == 0 && lane == 0 && h == 0) LS_TRACE(4, p);
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(bar(B_P_FULL + wg));
-            if (quad == 0 && lane == 0) LS_TRACE(5, p);
+            mbar_arrive(bar(B_P_FULL + b));
+            if (quad == 0 && lane == 0 && h == 0) LS_TRACE(5, p);
         }
         // ================= epilogue: normalised partial O + LSE =================
         const int Rtot = d.q_rows * G;
@@ -634,86 +676,97 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
             tc_fence_after();
         }
         auto part_base = [&](int sl, int rp) { return (static_cast<size_t>(d.part_offset + sl) * d.n_kv_heads + kvh) * Rtot + rp; };
+        // exchange the row states: m_ref per accumulator (the same in both halves), l per (accumulator, half)
+        float* st_m = xch;                                           // [2][128]   (xch is dead: every pair barrier has been passed)
+        float* st_l = xch + 2 * 128;                                 // [2][2][128]
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (h == 0) st_m[b * 128 + row] = m_ref;
+        st_l[(b * 2 + h) * 128 + row] = l;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        // The normalised rows go through shared memory (Q / K / V space is free: every MMA has completed) so that the
+        // global stores are whole 512-byte rows per warp instruction instead of 32 scattered 16-byte pieces - the
+        // direct version spent 14 000 cycles per heavy CTA in the LSU (profiles/r02_*).
+        float* stage = reinterpret_cast<float*>(smem);               // [row tile][128 rows][OUT_STRIDE]
+        int n_stage = 0;                                             // staged row tiles
         if (NR == 2) {
-            // warpgroup = row tile: (m_ref, l) and the accumulator are complete as they stand
+            // accumulator b = row tile b: complete as it stands; the two halves of the warpgroup pair stage 64 columns each
             const int rp = rp0 + row;
-            const float inv = l > 0.f ? 1.f / l : 0.f;
-            const size_t base = part_base(slot, rp);
-            if (rp < R) d.part_lse[base] = inv > 0.f ? (m_ref + log2f(l)) * 0.6931471805599453f : -INFINITY;
+            const float lt = st_l[(b * 2) * 128 + row] + st_l[(b * 2 + 1) * 128 + row];
+            const float inv = lt > 0.f ? 1.f / lt : 0.f;
+            if (h == 0 && rp < R) d.part_lse[part_base(slot, rp)] = inv > 0.f ? (m_ref + log2f(lt)) * 0.6931471805599453f : -INFINITY;
             if (warp_valid) {                             // warp-uniform (tcgen05.ld is warp-collective)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     uint32_t ov[32];
                     if (n_pairs > 0) {
-                        LS_TMEM_LD32(o_addr + c * 32, ov);
+                        LS_TMEM_LD32(o_half + c * 32, ov);
                         tmem_wait_ld();
                     }
                     if (inv == 0.f) {                     // no key seen (or no tile at all): the accumulator holds stale bits
 #pragma unroll
                         for (int e = 0; e < 32; ++e) ov[e] = 0u;
                     }
-                    if (rp < R) {
-                        float* po = d.part_o + base * 128 + c * 32;
+                    float* ps = stage + (b * 128 + row) * OUT_STRIDE + h * 64 + c * 32;
 #pragma unroll
-                        for (int e = 0; e < 32; e += 4)
-                            *reinterpret_cast<float4*>(po + e) =
-                                make_float4(__uint_as_float(ov[e]) * inv, __uint_as_float(ov[e + 1]) * inv,
-                                            __uint_as_float(ov[e + 2]) * inv, __uint_as_float(ov[e + 3]) * inv);
-                    }
+                    for (int e = 0; e < 32; e += 4)
+                        *reinterpret_cast<float4*>(ps + e) =
+                            make_float4(__uint_as_float(ov[e]) * inv, __uint_as_float(ov[e + 1]) * inv,
+                                        __uint_as_float(ov[e + 2]) * inv, __uint_as_float(ov[e + 3]) * inv);
                 }
             }
+            n_stage = 2;
         } else {
-            // One (or no) live row tile: the two warpgroups hold partial states of the SAME rows over alternate key
-            // tiles.  Exchange (m, l) through shared memory, then each warpgroup merges and writes 64 of the 128
-            // output columns.  Row tiles without live rows / CTAs without keys write empty partials.
-            st_m[wg * 128 + row] = m_ref;
-            st_l[wg * 128 + row] = l;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float m0 = st_m[row], m1 = st_m[128 + row], l0 = st_l[row], l1 = st_l[128 + row];
+            // One (or no) live row tile: the two accumulators hold partial states of the SAME rows over alternate key
+            // tiles.  Merge them; each of the four warpgroups stages 32 of the 128 output columns.  Row tiles without
+            // live rows / CTAs without keys write empty partials.
+            const float m0 = st_m[row], m1 = st_m[128 + row];
+            const float l0 = st_l[row] + st_l[128 + row], l1 = st_l[256 + row] + st_l[384 + row];
             const float m = fmaxf(m0, m1);
             const float a0 = l0 > 0.f ? fast_exp2(m0 - m) : 0.f, a1 = l1 > 0.f ? fast_exp2(m1 - m) : 0.f;
             const float lt = l0 * a0 + l1 * a1;
             const float inv = lt > 0.f ? 1.f / lt : 0.f;
             const float w0 = a0 * inv, w1 = a1 * inv;
-            for (int re = 0; re < nr_out; ++re) {
-                const bool live = re == 0 && NR == 1 && n_pairs > 0;
-                const int rp = (rt0 + re) * 128 + row;
-                const size_t base = part_base(slot, rp);
-                if (wg == 0 && rp < R) {
-                    d.part_lse[base] = (live && inv > 0.f) ? (m + log2f(lt)) * 0.6931471805599453f : -INFINITY;
-                    if (empty_slot >= 0) d.part_lse[part_base(empty_slot, rp)] = -INFINITY;
+            const bool live = NR == 1 && n_pairs > 0;
+            const int rp = rt0 * 128 + row;
+            if (wgi == 0 && rp < R) {
+                d.part_lse[part_base(slot, rp)] = (live && inv > 0.f) ? (m + log2f(lt)) * 0.6931471805599453f : -INFINITY;
+                if (empty_slot >= 0) d.part_lse[part_base(empty_slot, rp)] = -INFINITY;
+            }
+            if (rt0 * 128 + quad * 32 < R) {              // warp-uniform
+                const int col = wgi * 32;
+                uint32_t o0[32], o1[32];
+                if (live) {
+                    LS_TMEM_LD32(lane_addr + COL_O + col, o0);
+                    LS_TMEM_LD32(lane_addr + COL_O + 128 + col, o1);
+                    tmem_wait_ld();
                 }
-                if ((rt0 + re) * 128 + quad * 32 < R) {   // warp-uniform
+                float* ps = stage + row * OUT_STRIDE + col;
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int col = wg * 64 + c * 32;
-                        uint32_t o0[32], o1[32];
-                        if (live) {
-                            LS_TMEM_LD32(lane_addr + COL_O + col, o0);
-                            LS_TMEM_LD32(lane_addr + COL_O + 128 + col, o1);
-                            tmem_wait_ld();
-                        }
+                for (int e = 0; e < 32; e += 4) {
+                    float x[4];
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            // an accumulator that never received a PV holds stale TMEM bits: select, do not multiply
-                            const float x0 = (live && w0 > 0.f) ? __uint_as_float(o0[e]) * w0 : 0.f;
-                            const float x1 = (live && w1 > 0.f) ? __uint_as_float(o1[e]) * w1 : 0.f;
-                            o0[e] = __float_as_uint(x0 + x1);
-                        }
-                        if (rp < R) {
-                            float* po = d.part_o + base * 128 + col;
-#pragma unroll
-                            for (int e = 0; e < 32; e += 4)
-                                *reinterpret_cast<float4*>(po + e) = make_float4(__uint_as_float(o0[e]), __uint_as_float(o0[e + 1]),
-                                                                                __uint_as_float(o0[e + 2]), __uint_as_float(o0[e + 3]));
-                            if (empty_slot >= 0) {
-                                float* pe = d.part_o + part_base(empty_slot, rp) * 128 + col;
-#pragma unroll
-                                for (int e = 0; e < 32; e += 4) *reinterpret_cast<float4*>(pe + e) = make_float4(0.f, 0.f, 0.f, 0.f);
-                            }
-                        }
+                    for (int u = 0; u < 4; ++u) {
+                        // an accumulator that never received a PV holds stale TMEM bits: select, do not multiply
+                        const float x0 = (live && w0 > 0.f) ? __uint_as_float(o0[e + u]) * w0 : 0.f;
+                        const float x1 = (live && w1 > 0.f) ? __uint_as_float(o1[e + u]) * w1 : 0.f;
+                        x[u] = x0 + x1;
                     }
+                    *reinterpret_cast<float4*>(ps + e) = make_float4(x[0], x[1], x[2], x[3]);
                 }
+            }
+            n_stage = nr_out > 0 ? 1 : 0;
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        // coalesced write-out: one staged row (512 bytes) per warp instruction
+        {
+            const int sw = warp - 4;                                 // 0..15
+            for (int r = sw; r < n_stage * 128; r += 16) {
+                const int rp = rt0 * 128 + r;
+                if (rp >= R) break;                                  // rows ascend with r: nothing live behind
+                const float4 v = *reinterpret_cast<const float4*>(stage + r * OUT_STRIDE + lane * 4);
+                *reinterpret_cast<float4*>(d.part_o + part_base(slot, rp) * 128 + lane * 4) = v;
+                if (empty_slot >= 0)
+                    *reinterpret_cast<float4*>(d.part_o + part_base(empty_slot, rp) * 128 + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         tc_fence_before();

@@ -30,7 +30,7 @@ lib.ls_debug_set_trace.restype = C.c_int
 lib.ls_debug_set_trace.argtypes = [C.c_void_p]
 lib.ls_debug_set_flags.restype = C.c_int
 lib.ls_debug_set_flags.argtypes = [C.c_int]
-assert lib.ls_debug_set_flags(int(os.environ.get("DBG", 0))) == 0
+assert lib.ls_debug_set_flags(int(os.environ.get("DBG", 0)) | (int(os.environ.get("BX", 0)) << 16)) == 0   # BX = traced blockIdx.x
 buf = torch.zeros(8 * 512, dtype=torch.int64, device="cuda")
 assert lib.ls_debug_set_trace(C.c_void_p(buf.data_ptr())) == 0
 sys.argv = [sys.argv[0]] + (sys.argv[1:] or ["131072"]) + ["2"]
@@ -44,6 +44,12 @@ for t in range(lo, hi):
     print(f"{t:4d}  " + "  ".join(f"{int(ev[e, t]) - t0:9d}" for e in range(6)))
 import numpy as np  # noqa: E402
 e = ev.numpy().astype(np.int64)
+entry, done = int(e[7, 511]), int(e[7, 510])
+nz = e[2][e[2] != 0]
+lastp = e[5][:510][e[5][:510] != 0]
+if entry and nz.size:
+    print(f"CTA bx={os.environ.get('BX', 0)}: kernel entry -> first S_FULL seen {int(nz[0]) - entry} cycles; last P arrived -> epilogue written "
+          f"{done - int(lastp.max()) if lastp.size else 0}; entry -> epilogue written {done - entry}")
 valid = int((e[0] != 0).sum())
 sl = slice(20, max(valid - 10, 22))
 print(f"MMA warp (per PAIR of steps, {valid} pairs traced):")
