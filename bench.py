@@ -80,7 +80,9 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 25 ms; stop(t0, t1) keeps the samples that arrived while the
+    GPU was running the benchmark rounds (nvidia-smi needs ~1 s to deliver its first line, so it is started well
+    before the timed region and the warm-up replays - the identical workload - count as "under load")."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -91,31 +93,39 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception as e:  # noqa: BLE001
             log("clock sampler unavailable:", e)
 
+    def wait_first(self, timeout=5.0):
+        t_end = time.time() + timeout
+        while not self.lines and time.time() < t_end:
+            time.sleep(0.02)
+
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.06)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if (t0 is not None and ts < t0) or (t1 is not None and ts > t1 + 0.03):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
             try:
                 sm.append(float(f[0]))
                 mx = float(f[1])
+                power.append(float(f[2]))
             except ValueError:
                 continue
             for n, v in zip(names, f[3:7]):
@@ -123,7 +133,8 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(power) if power else None,
+                "window": "samples taken while the warm-up and timed graph replays ran (same workload back to back)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -273,7 +284,8 @@ def main():
     log(f"[rank {rank}] weights ready in {time.time() - t0:.1f} s")
     ids_host = synthetic_prompt(dims.vocab, PROMPT, seed=0).pin_memory()
     plen = torch.tensor([PROMPT])
-    max_gen = (2 * (W + K) + 6) * (gamma + 1) + 64
+    MAX_WARM = 100                                   # upper bound of the device-timed warm-up replays (see below)
+    max_gen = (2 * (W + K) + MAX_WARM + 6) * (gamma + 1) + 64
 
     def barrier():
         if world > 1:
@@ -301,21 +313,27 @@ def main():
 
     # ---------------- (B) device-resident: K graph replays between CUDA events ----------------
     eng, graph = m.eng, m.last_graph
+    exchange = eng.exchange
     assert graph is not None, "CUDA graph capture is required for the device-timed number"
     st = eng.st
     st["counters"][3] = 0                    # a set stop flag would turn the replayed rounds' acceptance into no-ops
-    for _ in range(W):
+    sampler.start()
+    sampler.wait_first()
+    barrier()
+    t_load0 = time.time()
+    # warm-up: at least W rounds, and at least 0.3 s of the identical workload so that the clock samples describe it
+    n_warm = min(max(W, int(0.3 / max(e2e_time / K, 1e-4))), MAX_WARM)
+    for _ in range(n_warm):
         graph.replay()
     barrier()
     c0 = st["counters"].clone()
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(K):
         graph.replay()
     ev1.record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_load0, time.time())
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -409,6 +427,7 @@ def main():
         "config": {"workload": f"{MODEL} widths, random-init bf16 weights, {PROMPT}-token synthetic prompt, tree "
                                f"{' '.join(map(str, TREE))}, bsz 1, T=0",
                    "parallelism": "single GPU" if world == 1 else f"prefix KV sequence-sharded over {world} GPUs, weights replicated",
+                   "exchange": exchange,
                    "l2": "inputs larger than L2: every round streams all weights and the whole KV cache (> 30 GB)",
                    "accepted_len_tau": tau, "draft_scale": DRAFT_SCALE},
         "clocks": clocks,

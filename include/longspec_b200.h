@@ -123,6 +123,35 @@ int ls_attn_combine(const ls_attn_desc* d, void* stream);
 int ls_attn_reduce(const ls_attn_desc* d, float* dst_o, float* dst_lse, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Sequence-sharded prefix KV over the GPUs of one node: the per-call exchange of the ranks' partials fused into
+ * the two merge kernels over NVLink peer memory (no reference counterpart: the reference is single-GPU; SURVEY.md
+ * section 8(e), option C).  Every rank owns an exchange buffer that all ranks have mapped (symmetric memory):
+ *     O      [2 parities][world blocks][block_o]   fp32      LSE [2 parities][world blocks][block_lse] fp32
+ *     flags  [world] uint32: epoch of the last block received from each source rank
+ * ls_attn_reduce_push = ls_attn_reduce whose result goes straight into block `rank` of EVERY rank's buffer (peer
+ * stores), followed by one release-store of the epoch into every rank's flag for this source.
+ * ls_attn_combine_wait = ls_attn_combine over the `world` blocks of this rank's own buffer, after an acquire-spin
+ * until every source's flag shows the current epoch.  Blocks alternate between two parities so that a fast rank's
+ * next call cannot overwrite blocks a slow rank is still merging (a rank can be at most one call ahead: its call c+2
+ * needs every other rank's block c+1, which is pushed after that rank finished merging call c).
+ * The epoch lives in device memory (local_sync[0]) and is advanced by the combine kernel, so both calls can be
+ * captured in a CUDA graph and replayed.  The merge order is rank order on every rank: bit-identical outputs.
+ * ---------------------------------------------------------------------------------------- */
+#define LS_MAX_PEERS 8
+typedef struct ls_xchg {
+    float* peer_o[LS_MAX_PEERS];        /* rank r's O exchange buffer as mapped into THIS process */
+    float* peer_lse[LS_MAX_PEERS];
+    uint32_t* peer_flags[LS_MAX_PEERS]; /* rank r's flag array [world] */
+    uint32_t* local_sync;               /* this rank only: [0] epoch, [1] reduce ticket, [2] combine ticket (zeroed once) */
+    int64_t block_o;                    /* floats per O block (capacity >= n_kv_heads * q_rows * group * 128 of any call) */
+    int64_t block_lse;                  /* floats per LSE block */
+    int32_t rank, world;
+} ls_xchg;
+int ls_attn_reduce_push(const ls_attn_desc* d, const ls_xchg* x, void* stream);
+/* d->part_o / part_lse / n_parts_total are ignored: the kernel merges the `world` blocks of this rank's buffer */
+int ls_attn_combine_wait(const ls_attn_desc* d, const ls_xchg* x, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * RoPE + KV append.  Replaces apply_rotary_pos_emb (llama.py:378, llama_glide.py:256,294) and
  * the cache scatters K_Cache[b, cache_lens + r] = k (llama.py:396-399, llama_glide.py:312-315)
  * and flash_attn_with_kvcache's in-place append (llama_glide.py:261).

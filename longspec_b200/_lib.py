@@ -42,6 +42,16 @@ class TreeState(C.Structure):
     ]
 
 
+LS_MAX_PEERS = 8
+
+
+class Xchg(C.Structure):
+    _fields_ = [
+        ("peer_o", vp * LS_MAX_PEERS), ("peer_lse", vp * LS_MAX_PEERS), ("peer_flags", vp * LS_MAX_PEERS),
+        ("local_sync", vp), ("block_o", i64), ("block_lse", i64), ("rank", i32), ("world", i32),
+    ]
+
+
 _SIGS = {
     "ls_version": (i32, []),
     "ls_last_error": (C.c_char_p, []),
@@ -51,6 +61,8 @@ _SIGS = {
     "ls_attn_partial_tc": (i32, [C.POINTER(AttnDesc), i32, vp]),
     "ls_attn_combine": (i32, [C.POINTER(AttnDesc), vp]),
     "ls_attn_reduce": (i32, [C.POINTER(AttnDesc), vp, vp, vp]),
+    "ls_attn_reduce_push": (i32, [C.POINTER(AttnDesc), C.POINTER(Xchg), vp]),
+    "ls_attn_combine_wait": (i32, [C.POINTER(AttnDesc), C.POINTER(Xchg), vp]),
     "ls_rope_append": (i32, [vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, i32, i32, i32, vp]),
     "ls_round_begin": (i32, [C.POINTER(TreeState), vp]),
     "ls_grow_workspace_bytes": (i64, [i32, i32]),

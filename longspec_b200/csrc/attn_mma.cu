@@ -394,6 +394,138 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const ls_attn_desc d,
     *reinterpret_cast<uint2*>(out) = pk;
 }
 
+// ---- multi-GPU: reduce + push to every peer / wait + combine (see include/longspec_b200.h, ls_xchg) ----------------
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// One warp per (packed row, kv head): merge this launch's own slots (like attn_combine_kernel<REDUCE>) and store the
+// normalised fp32 row + LSE into block `rank` of EVERY rank's exchange buffer; the last CTA publishes the epoch.
+__global__ void __launch_bounds__(256) attn_reduce_push_kernel(const ls_attn_desc d, const ls_xchg x) {
+    const int G = d.n_heads / d.n_kv_heads;
+    const int Rtot = d.q_rows * G;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(x.local_sync);
+    const int par = epoch & 1;
+    if (warp_global < Rtot * d.n_kv_heads) {
+        const int kvh = warp_global / Rtot, r = warp_global - kvh * Rtot;
+        const int i = r / G;
+        const int n_q = min(*d.n_q_ptr, d.q_rows);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float lse_out = -INFINITY;
+        if (i < n_q) {
+            const size_t stride = static_cast<size_t>(d.n_kv_heads) * Rtot;        // between parts, in rows
+            const size_t row0 = static_cast<size_t>(kvh) * Rtot + r + d.part_offset * stride;
+            const int P = d.n_splits;
+            float mx = -INFINITY;
+            for (int p = lane; p < P; p += 32) mx = fmaxf(mx, d.part_lse[p * stride + row0]);
+            mx = warp_max(mx);
+            float wsum = 0.f;
+            if (mx != -INFINITY) {
+                for (int p0 = 0; p0 < P; p0 += 32) {
+                    const int p = p0 + lane;
+                    const float lse = p < P ? d.part_lse[p * stride + row0] : -INFINITY;
+                    const float w_mine = lse == -INFINITY ? 0.f : __expf(lse - mx);
+                    wsum += w_mine;
+                    const int cnt = min(32, P - p0);
+                    const float* base = d.part_o + (p0 * stride + row0) * kD + lane * 4;
+#pragma unroll 4
+                    for (int k = 0; k < cnt; ++k) {
+                        const float w = __shfl_sync(0xffffffffu, w_mine, k);
+                        const float4 v = *reinterpret_cast<const float4*>(base + k * stride * kD);
+                        acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                        acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                    }
+                }
+                wsum = warp_sum(wsum);
+                const float inv = 1.f / wsum;
+                acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+                lse_out = mx + logf(wsum);
+            }
+        }
+        const size_t row = static_cast<size_t>(kvh) * Rtot + r;
+        const size_t blk = static_cast<size_t>(par) * x.world + x.rank;
+        for (int p = 0; p < x.world; ++p) {
+            *reinterpret_cast<float4*>(x.peer_o[p] + blk * x.block_o + row * kD + lane * 4) = acc;
+            if (lane == 0) x.peer_lse[p][blk * x.block_lse + row] = lse_out;
+        }
+    }
+    // publish: every CTA's stores must be visible system-wide before the flag moves
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t ticket = atomicAdd(x.local_sync + 1, 1u);
+        if (ticket == gridDim.x - 1) {
+            x.local_sync[1] = 0;
+            __threadfence_system();
+            for (int p = 0; p < x.world; ++p) st_release_sys(x.peer_flags[p] + x.rank, epoch + 1);
+        }
+    }
+}
+
+// Wait until every source's block of the current epoch has arrived, merge the `world` blocks in rank order, write `out`.
+template <typename T>
+__global__ void __launch_bounds__(256) attn_combine_wait_kernel(const ls_attn_desc d, const ls_xchg x) {
+    const int G = d.n_heads / d.n_kv_heads;
+    const int Rtot = d.q_rows * G;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(x.local_sync);
+    const int par = epoch & 1;
+    if (threadIdx.x < x.world) {
+        const uint32_t* flag = x.peer_flags[x.rank] + threadIdx.x;
+        while (static_cast<int32_t>(ld_acquire_sys(flag) - (epoch + 1)) < 0) { }
+    }
+    __syncthreads();
+    if (warp_global < Rtot * d.n_kv_heads) {
+        const int kvh = warp_global / Rtot, r = warp_global - kvh * Rtot;
+        const int i = r / G, g = r - i * G;
+        const int n_q = min(*d.n_q_ptr, d.q_rows);
+        T* out = reinterpret_cast<T*>(d.out) + (static_cast<size_t>(i) * d.n_heads + kvh * G + g) * kD + lane * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n_q) {
+            const size_t row = static_cast<size_t>(kvh) * Rtot + r;
+            const float* bo = x.peer_o[x.rank] + static_cast<size_t>(par) * x.world * x.block_o;
+            const float* bl = x.peer_lse[x.rank] + static_cast<size_t>(par) * x.world * x.block_lse;
+            const int P = x.world;                                    // <= 8: one LSE per lane
+            const float lse = lane < P ? __ldcg(bl + lane * x.block_lse + row) : -INFINITY;
+            const float mx = warp_max(lse);
+            if (mx != -INFINITY) {
+                const float w_mine = lse == -INFINITY ? 0.f : __expf(lse - mx);
+                const float wsum = warp_sum(w_mine);
+                for (int k = 0; k < P; ++k) {
+                    const float w = __shfl_sync(0xffffffffu, w_mine, k);
+                    const float4 v = __ldcg(reinterpret_cast<const float4*>(bo + k * x.block_o + row * kD + lane * 4));
+                    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                    acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                }
+                const float inv = 1.f / wsum;
+                acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+            }
+        }
+        uint2 pk;
+        pk.x = Num<T>::pack(acc.x, acc.y);
+        pk.y = Num<T>::pack(acc.z, acc.w);
+        *reinterpret_cast<uint2*>(out) = pk;
+    }
+    // the last CTA advances the epoch (the next kernel in the stream reads it)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t ticket = atomicAdd(x.local_sync + 2, 1u);
+        if (ticket == gridDim.x - 1) {
+            x.local_sync[2] = 0;
+            x.local_sync[0] = epoch + 1;
+        }
+    }
+}
+
 static int validate(const ls_attn_desc* d) {
     LS_REQUIRE(d != nullptr, "ls_attn: null descriptor");
     LS_REQUIRE(d->q && d->out && d->k_pool && d->v_pool && d->page_table && d->kv_len_ptr && d->n_q_ptr,
@@ -463,4 +595,46 @@ extern "C" int ls_attn_reduce(const ls_attn_desc* d, float* dst_o, float* dst_ls
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     attn_combine_kernel<__nv_bfloat16, true><<<blocks, 256, 0, st>>>(*d, dst_o, dst_lse);   // dtype-independent (fp32 in, fp32 out)
     return check_launch("ls_attn_reduce");
+}
+
+static int validate_xchg(const ls_attn_desc* d, const ls_xchg* x, const char* what) {
+    using namespace ls;
+    LS_REQUIRE(x && x->local_sync && x->world >= 1 && x->world <= LS_MAX_PEERS && x->rank >= 0 && x->rank < x->world,
+               "%s: bad exchange descriptor", what);
+    const int G = d->n_heads / d->n_kv_heads;
+    const int64_t rows = static_cast<int64_t>(d->n_kv_heads) * d->q_rows * G;
+    LS_REQUIRE(x->block_o >= rows * 128 && x->block_lse >= rows, "%s: exchange blocks too small for %lld rows", what,
+               static_cast<long long>(rows));
+    for (int p = 0; p < x->world; ++p)
+        LS_REQUIRE(x->peer_o[p] && x->peer_lse[p] && x->peer_flags[p], "%s: null peer pointer (rank %d)", what, p);
+    return LS_OK;
+}
+
+extern "C" int ls_attn_reduce_push(const ls_attn_desc* d, const ls_xchg* x, void* stream) {
+    using namespace ls;
+    int rc = validate(d);
+    if (rc != LS_OK) return rc;
+    rc = validate_xchg(d, x, "ls_attn_reduce_push");
+    if (rc != LS_OK) return rc;
+    const int G = d->n_heads / d->n_kv_heads;
+    const int warps = d->q_rows * G * d->n_kv_heads;
+    attn_reduce_push_kernel<<<(warps + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(*d, *x);
+    return check_launch("ls_attn_reduce_push");
+}
+
+extern "C" int ls_attn_combine_wait(const ls_attn_desc* d, const ls_xchg* x, void* stream) {
+    using namespace ls;
+    LS_REQUIRE(d && d->out && d->n_q_ptr && d->n_kv_heads >= 1 && d->n_heads % d->n_kv_heads == 0 && d->q_rows >= 1,
+               "ls_attn_combine_wait: bad descriptor");
+    LS_REQUIRE(d->dtype == LS_F16 || d->dtype == LS_BF16, "ls_attn_combine_wait: bad dtype %d", d->dtype);
+    int rc = validate_xchg(d, x, "ls_attn_combine_wait");
+    if (rc != LS_OK) return rc;
+    const int G = d->n_heads / d->n_kv_heads;
+    const int warps = d->q_rows * G * d->n_kv_heads;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d->dtype == LS_F16)
+        attn_combine_wait_kernel<__half><<<(warps + 7) / 8, 256, 0, st>>>(*d, *x);
+    else
+        attn_combine_wait_kernel<__nv_bfloat16><<<(warps + 7) / 8, 256, 0, st>>>(*d, *x);
+    return check_launch("ls_attn_combine_wait");
 }

@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -285,7 +286,24 @@ class Engine:
         self.part_lse = torch.empty(max_parts * d.kv_heads * rows_max, dtype=torch.float32, device=dev)
         # multi-GPU exchange blocks: ONE locally reduced (O, lse) partial per rank and attention call
         self.xchg_o = self.xchg_lse = None
-        if world > 1:
+        self.peer = None
+        if world > 1 and os.environ.get("LONGSPEC_XCHG", "peer") != "nccl":
+            # fused exchange over NVLink peer memory; falls back to the NCCL all-gather only if symmetric memory cannot
+            # be set up on this system (the reason is kept in self.peer_error and reported by bench.py)
+            try:
+                from .parallel import get_peer_exchange
+                self.peer = get_peer_exchange(d.kv_heads * rows_max, dev, self.group)
+            except Exception as e:  # noqa: BLE001
+                self.peer_error = f"{type(e).__name__}: {e}"
+            # all ranks or none: a rank that fell back alone would wait for collectives the others never issue
+            import torch.distributed as dist
+            ok = torch.tensor([1 if self.peer is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok) == 0:
+                self.peer = None
+        self.exchange = "single GPU" if world == 1 else ("peer memory (NVLink stores + flags)" if self.peer is not None else
+                                                         "NCCL all-gather" + (f" ({self.peer_error})" if getattr(self, "peer_error", None) else ""))
+        if world > 1 and self.peer is None:
             self.xchg_o = torch.empty(world * d.kv_heads * rows_max * 128, dtype=torch.float32, device=dev)
             self.xchg_lse = torch.empty(world * d.kv_heads * rows_max, dtype=torch.float32, device=dev)
             self.send_o = torch.empty(d.kv_heads * rows_max * 128, dtype=torch.float32, device=dev)
@@ -319,6 +337,13 @@ class Engine:
         sharded = kw.get("sharded", True)
         self.descs.append(a)
         _lib.call("ls_attn_partial", C.byref(a), _stream())
+        if sharded and self.shard.world > 1 and self.peer is not None:
+            # one fused compute + exchange kernel pair: merge the local slots and push the block to every peer, then
+            # wait for every peer's block and merge them in rank order
+            _lib.call("ls_attn_reduce_push", C.byref(a), self.peer.ref, _stream())
+            _lib.call("ls_attn_combine_wait", C.byref(a), self.peer.ref, _stream())
+            self.launches += 3
+            return
         if sharded and self.shard.world > 1:
             a = self._exchange_partials(a, q_rows)
         _lib.call("ls_attn_combine", C.byref(a), _stream())

@@ -324,6 +324,13 @@ class LlamaGlide:
         spec_mask = torch.zeros(1, max_gen_len, dtype=torch.int64, device=self.device)
         return st["output_ids"].clone()[None], count, num, elapsed_time, spec_mask
 
+    # -------------------------------------------------------------- operator seam (llama_glide.py:1128-1175)
+    def tree_verification(self, input_ids, output_ids, tree_mask, cache_lens, non_leaf_len, K_Cache=None, V_Cache=None):
+        """Reference-shaped greedy tree verification on dense tensors (the decode loop itself calls ls_tree_accept on
+        its device-resident state).  See longspec_b200.seams.tree_verification."""
+        from .seams import tree_verification
+        return tree_verification(input_ids, output_ids, tree_mask, cache_lens, non_leaf_len, K_Cache, V_Cache)
+
     # -------------------------------------------------------------- other driver methods
     def spec_generate(self, *a, **k):
         raise NotImplementedError("--method seq (llama_glide.py:621-774) is outside the tree-spec hot path")

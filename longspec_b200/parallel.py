@@ -38,3 +38,54 @@ def exchange_partials(part_o: torch.Tensor, part_lse: torch.Tensor, n_o: int, n_
     else:
         dist.all_gather_into_tensor(o_all, o_mine, group=group)
         dist.all_gather_into_tensor(l_all, l_mine, group=group)
+
+
+class PeerExchange:
+    """The exchange of SURVEY.md section 8(e) option C: every rank's merge kernels store their (O, lse) block straight into
+    every peer's exchange buffer over NVLink (ls_attn_reduce_push) and spin on per-source flags before merging
+    (ls_attn_combine_wait) - no NCCL launch per attention call.  The buffers are torch symmetric memory (one allocation
+    per rank, mapped into every process of the group by `rendezvous`); see include/longspec_b200.h (ls_xchg) for the
+    layout and the epoch / parity protocol.  Raises if symmetric memory is unavailable: the caller then keeps the NCCL
+    all-gather (LONGSPEC_XCHG=nccl forces that)."""
+
+    def __init__(self, rows_max: int, device, group):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world > _lib.LS_MAX_PEERS:
+            raise RuntimeError(f"peer exchange supports up to {_lib.LS_MAX_PEERS} ranks")
+        self.block_o = rows_max * 128
+        self.block_lse = (rows_max + 31) // 32 * 32
+        n_o, n_l, n_f = 2 * world * self.block_o, 2 * world * self.block_lse, 64
+        self.buf = symm_mem.empty(n_o + n_l + n_f, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        self.handle = symm_mem.rendezvous(self.buf, group.group_name if hasattr(group, "group_name") else group)
+        dist.barrier(group)                                    # every rank's flags are zero before anybody pushes
+        self.local_sync = torch.zeros(4, dtype=torch.int32, device=device)
+        x = _lib.Xchg()
+        ptrs = list(self.handle.buffer_ptrs)
+        for r in range(world):
+            x.peer_o[r] = ptrs[r]
+            x.peer_lse[r] = ptrs[r] + 4 * n_o
+            x.peer_flags[r] = ptrs[r] + 4 * (n_o + n_l)
+        x.local_sync = self.local_sync.data_ptr()
+        x.block_o, x.block_lse, x.rank, x.world = self.block_o, self.block_lse, rank, world
+        self.x = x
+        self.ref = C.byref(x)
+
+
+_PEER_CACHE = {}
+
+
+def get_peer_exchange(rows_max: int, device, group) -> PeerExchange:
+    """One exchange buffer per (group, device), grown on demand and reused by every generation of the process: the
+    allocation and the rendezvous are collectives, and the epoch simply keeps counting (all ranks issue the same
+    sequence of exchange calls)."""
+    key = (id(group), str(device))
+    cur = _PEER_CACHE.get(key)
+    if cur is None or cur.block_o < rows_max * 128:
+        cur = PeerExchange(rows_max, device, group)
+        _PEER_CACHE[key] = cur
+    return cur

@@ -1,0 +1,116 @@
+"""-m gpu: the UNMODIFIED reference driver (longspec/test/inference_long-bench.py) run against the drop-in.
+
+The driver file is executed as shipped (runpy) from $LONGSPEC_REF_DIR or /root/reference - the test is skipped where the
+reference tree is not mounted (e.g. the GPU box of the round-end run).  `from llama_glide import LlamaGlide` resolves to
+dropin/llama_glide.py; the hub ids the driver passes ("lmsys/vicuna-7b-v1.5-16k", "sail/longspec-vicuna-7b-v1.5-16k")
+resolve through a LOCAL Hugging Face cache that the test fills with a toy-width checkpoint (real AutoConfig, real
+snapshot lookup, safetensors in the reference's key names); only the tokenizer is a stub (no tokenizer files offline)
+and the LongBench .jsonl is synthetic."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ref_dir():
+    for d in (os.environ.get("LONGSPEC_REF_DIR"), "/root/reference"):
+        if d and os.path.exists(os.path.join(d, "longspec", "test", "inference_long-bench.py")):
+            return d
+    return None
+
+
+def make_fake_hub(home, dims, seed=5):
+    """A Hugging Face cache holding the two repos the driver names for --model_name vicuna7b, at toy widths."""
+    from safetensors.torch import save_file
+    from longspec_b200.synthetic import synthetic_state_dict
+    W = synthetic_state_dict(dims, seed=seed, dtype=torch.float16)
+    cfg = {"architectures": ["LlamaForCausalLM"], "model_type": "llama", "hidden_size": dims.hidden,
+           "num_attention_heads": dims.heads, "num_key_value_heads": dims.kv_heads, "num_hidden_layers": dims.layers,
+           "intermediate_size": dims.ffn, "vocab_size": dims.vocab, "rms_norm_eps": dims.rms_eps, "rope_theta": dims.rope_theta,
+           "rope_scaling": {"type": "linear", "factor": 4.0}, "max_position_embeddings": 16384, "hidden_act": "silu",
+           "head_dim": 128, "bos_token_id": 1, "eos_token_id": 2, "pad_token_id": 0, "tie_word_embeddings": False}
+    repos = {"lmsys/vicuna-7b-v1.5-16k": {k: v for k, v in W.items() if not k.startswith("glide.")},
+             "sail/longspec-vicuna-7b-v1.5-16k": {k[len("glide."):]: v for k, v in W.items() if k.startswith("glide.")}}
+    for repo, sd in repos.items():
+        base = os.path.join(home, "hub", "models--" + repo.replace("/", "--"))
+        snap = os.path.join(base, "snapshots", "0123456789abcdef")
+        os.makedirs(snap)
+        os.makedirs(os.path.join(base, "refs"))
+        open(os.path.join(base, "refs", "main"), "w").write("0123456789abcdef")
+        json.dump(cfg, open(os.path.join(snap, "config.json"), "w"))
+        save_file({k: v.contiguous() for k, v in sd.items()}, os.path.join(snap, "model.safetensors"))
+    return W
+
+
+RUNNER = r'''
+import runpy, sys, torch, transformers
+
+class StubTokenizer:
+    """Deterministic stand-in for the HF tokenizer (no tokenizer files are reachable offline)."""
+    vocab = VOCAB
+    def __call__(self, text, return_tensors="pt", padding=True, padding_side="right"):
+        ids = [2 + (hash_(w) % (self.vocab - 4)) for w in text.split()]
+        return {"input_ids": torch.tensor([ids], dtype=torch.int64), "attention_mask": torch.ones(1, len(ids), dtype=torch.int64)}
+    def decode(self, ids):
+        return "IDS " + " ".join(str(int(i)) for i in ids)
+
+def hash_(w):
+    h = 2166136261
+    for ch in w.encode():
+        h = ((h ^ ch) * 16777619) & 0xffffffff
+    return h
+
+transformers.AutoTokenizer.from_pretrained = staticmethod(lambda *a, **k: StubTokenizer())
+sys.path.insert(0, DROPIN)
+sys.argv = ["inference_long-bench.py"] + ARGS
+runpy.run_path(DRIVER, run_name="__main__")
+'''
+
+
+def _run_driver(tmp_path, method):
+    ref = _ref_dir()
+    driver = os.path.join(ref, "longspec", "test", "inference_long-bench.py")
+    args = ["--model_name", "vicuna7b", "--method", method, "--task", "lcc", "--data_path_prefix", str(tmp_path),
+            "--test_length", "1", "--max_gen_len", "48", "--tree_shape", "4", "16", "16", "16", "16"]
+    runner = tmp_path / f"run_{method}.py"
+    runner.write_text(RUNNER.replace("VOCAB", "320").replace("DROPIN", repr(os.path.join(ROOT, "dropin")))
+                      .replace("ARGS", repr(args)).replace("DRIVER", repr(driver)))
+    env = dict(os.environ, HF_HOME=str(tmp_path / "hf"), HF_HUB_OFFLINE="1", TRANSFORMERS_OFFLINE="1",
+               PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), LONGSPEC_DTYPE="float16")
+    env.pop("HF_HUB_CACHE", None)
+    env.pop("TRANSFORMERS_CACHE", None)
+    res = subprocess.run([sys.executable, str(runner)], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + "\n" + res.stderr[-4000:]
+    return res.stdout
+
+
+def test_unmodified_reference_driver_runs_against_the_dropin(tmp_path):
+    if _ref_dir() is None:
+        pytest.skip("reference tree not mounted (set LONGSPEC_REF_DIR)")
+    from longspec_b200.synthetic import PRESETS
+    make_fake_hub(str(tmp_path / "hf"), PRESETS["tiny"])
+    words = " ".join(f"w{i % 97}x{i % 13}" for i in range(1500))            # > 1200 tokens: the driver drops shorter prompts (:122)
+    (tmp_path / "lcc.jsonl").write_text(json.dumps({"context": words + "\n"}) + "\n")
+    out_tree = _run_driver(tmp_path, "tree")
+    out_van = _run_driver(tmp_path, "vanilla")
+    # the driver's own summary lines (inference_long-bench.py:257-260): "<model> tree <T> <counts> <nums> <tau>", "... <time> <tok/s>"
+    m = re.search(r"vicuna7b tree 0\.0 (\S+) (\d+) ([0-9.]+)\s*\n+\s*vicuna7b tree 0\.0 ([0-9.eE+-]+) ([0-9.eE+-]+)", out_tree)
+    assert m, out_tree[-1500:]
+    nums, tau, secs, tps = int(m.group(2)), float(m.group(3)), float(m.group(4)), float(m.group(5))
+    assert nums >= 1 and 1.0 <= tau <= 6.0 and secs > 0 and tps > 0
+    mv = re.search(r"vicuna7b vanilla (\d+)\s*\n+\s*vicuna7b vanilla ([0-9.eE+-]+) ([0-9.eE+-]+)", out_van)
+    assert mv, out_van[-1500:]
+    # lossless: the tree run's decoded tokens are a prefix-compatible copy of the vanilla run's
+    ids_tree = [int(x) for x in re.findall(r"IDS ((?:-?\d+ ?)+)", out_tree)[-1].split()]
+    ids_van = [int(x) for x in re.findall(r"IDS ((?:-?\d+ ?)+)", out_van)[-1].split()]
+    n = int(float(m.group(1).replace("tensor(", "").split(",")[0])) + nums if "tensor" in m.group(1) else None
+    k = min(len([t for t in ids_tree if t != 151645]), 30)
+    assert ids_tree[:k] == ids_van[:k], (ids_tree[:40], ids_van[:40])
