@@ -217,6 +217,19 @@ int ls_tree_grow(const ls_tree_state* s, const void* logits, int32_t logits_fp32
                  int32_t vocab, int32_t level, int32_t level_begin, int32_t level_end, int32_t n_new,
                  void* workspace, void* stream);
 
+/* The same in two halves, for a vocab-sharded lm_head (multi-GPU; no reference counterpart): every rank computes the logits
+ * of a chunk-aligned slice of the vocabulary (chunk = 2048 ids; `logits` row stride `ld`, first column = id chunk0 * 2048)
+ * and ls_tree_grow_partial reduces it to per-chunk (max, sum exp, top-n_new) blocks of ls_grow_chunk_bytes() bytes each,
+ * written to ws_slice[0 .. n_chunks_local) with GLOBAL token ids; after the ranks' slices have been all-gathered into one
+ * workspace of n_chunks blocks (slices padded to equal length: blocks behind the end of the vocabulary are empty),
+ * ls_tree_grow_finish does the merges and the tree update - identically on every rank.
+ * ls_tree_grow == partial over the whole vocabulary + finish. */
+int64_t ls_grow_chunk_bytes(void);
+int ls_tree_grow_partial(const void* logits, int32_t logits_fp32, int32_t dtype, int32_t rows, int64_t ld, int32_t vocab,
+                         int32_t chunk0, int32_t n_chunks_local, int32_t n_new, void* ws_slice, void* stream);
+int ls_tree_grow_finish(const ls_tree_state* s, int32_t vocab, int32_t n_chunks, int32_t level, int32_t level_begin,
+                        int32_t level_end, int32_t n_new, const void* workspace, void* stream);
+
 /* Verify-input assembly (llama_glide.py:1077-1085, llama.py:575-577): draft_len += 1, veri_ids,
  * veri_pos, veri_bits, veri_rows, logit_rows. */
 int ls_build_verify(const ls_tree_state* s, void* stream);
@@ -225,6 +238,12 @@ int ls_build_verify(const ls_tree_state* s, void* stream);
  * llm_logits.argmax(-1) (llama_glide.py:1105) and the vanilla path's argmax (574). */
 int ls_argmax_rows(const void* logits, int32_t logits_fp32, int32_t dtype, int32_t rows, int32_t vocab,
                    int64_t* out, void* stream);
+
+/* Vocab-sharded form of the same: (value bits, GLOBAL index) int64 pairs per row over this rank's slice, then - on the
+ * all-gathered pairs [world][rows][2] - the merge by (value desc, index asc).  index -1 marks an empty slice. */
+int ls_argmax_rows_partial(const void* logits, int32_t logits_fp32, int32_t dtype, int32_t rows, int32_t vocab_local,
+                           int64_t ld, int32_t vocab_begin, int64_t* out_pairs, void* stream);
+int ls_argmax_merge(const int64_t* pairs, int32_t world, int32_t rows, int64_t* out, void* stream);
 
 /* Greedy tree verification + last-layer accepted-path KV compaction + counters
  * (llama_glide.py:1104-1116 and tree_verification 1128-1175).  llm_pred [fseq] int64.

@@ -67,6 +67,11 @@ _SIGS = {
     "ls_round_begin": (i32, [C.POINTER(TreeState), vp]),
     "ls_grow_workspace_bytes": (i64, [i32, i32]),
     "ls_tree_grow": (i32, [C.POINTER(TreeState), vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "ls_grow_chunk_bytes": (i64, []),
+    "ls_tree_grow_partial": (i32, [vp, i32, i32, i32, i64, i32, i32, i32, i32, vp, vp]),
+    "ls_tree_grow_finish": (i32, [C.POINTER(TreeState), i32, i32, i32, i32, i32, i32, vp, vp]),
+    "ls_argmax_rows_partial": (i32, [vp, i32, i32, i32, i32, i64, i32, vp, vp]),
+    "ls_argmax_merge": (i32, [vp, i32, i32, vp, vp]),
     "ls_build_verify": (i32, [C.POINTER(TreeState), vp]),
     "ls_argmax_rows": (i32, [vp, i32, i32, i32, i32, vp, vp]),
     "ls_tree_accept": (i32, [C.POINTER(TreeState), vp, vp, vp, vp, i32, i32, i32, i64, i32, vp]),

@@ -43,6 +43,12 @@ __global__ void round_begin_kernel(ls_tree_state s) {
 // Tree growth, phase A: per (row, vocab chunk): max, sum exp(x - max), local top-k by (value, index).
 constexpr int kChunk = 2048;
 constexpr int kGrowThreads = 256;
+constexpr int kMaxRowsB = 32;
+// Workspace = one fixed-size block per vocab chunk: { max[32 rows], sum[32 rows], val[32 rows][32], idx[32 rows][32] }.
+// Chunk-major so that the chunks a rank computed (vocab-sharded lm_head) are ONE
+// contiguous piece that a single all-gather moves; the capacities are the kernels' limits, not the call's sizes.
+constexpr int kBlkMax = 0, kBlkSum = kMaxRowsB, kBlkVal = 2 * kMaxRowsB, kBlkIdx = 2 * kMaxRowsB + kMaxRowsB * LS_MAX_TOPK;
+constexpr int kBlkWords = 2 * kMaxRowsB + 2 * kMaxRowsB * LS_MAX_TOPK;       // 2112 words = 8448 bytes
 
 template <typename T>
 __device__ __forceinline__ float load_logit(const void* p, size_t i, int fp32) {
@@ -50,20 +56,22 @@ __device__ __forceinline__ float load_logit(const void* p, size_t i, int fp32) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kGrowThreads) grow_phase_a(const void* logits, int fp32, int vocab, int n_chunks,
-                                                             int k, const int32_t* row_sel, float* ws_max,
-                                                             float* ws_sum, float* ws_val, int32_t* ws_idx) {
-    const int chunk = blockIdx.x, row = blockIdx.y;
-    const int src_row = row_sel ? *row_sel : row;       // level 0 reads row acc_num-1 of the logits
+// `logits` holds the columns [chunk0 * kChunk, ...) of the vocabulary (row stride ld): the whole vocabulary on one GPU,
+// a chunk-aligned slice per rank when the lm_head is vocab-sharded.  Block blockIdx.x of `ws` is chunk chunk0 + blockIdx.x;
+// candidate indices are GLOBAL vocabulary ids.
+__global__ void __launch_bounds__(kGrowThreads) grow_phase_a(const void* logits, int fp32, int vocab, int64_t ld, int chunk0,
+                                                             int k, float* ws) {
+    const int chunk = chunk0 + blockIdx.x, row = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int PER = kChunk / kGrowThreads;          // 8
     float v[PER];
     const int base = chunk * kChunk;
+    float* blk = ws + static_cast<size_t>(blockIdx.x) * kBlkWords;
     float mx = -INFINITY;
 #pragma unroll
     for (int e = 0; e < PER; ++e) {
         const int c = base + e * kGrowThreads + tid;
-        v[e] = c < vocab ? load_logit<T>(logits, static_cast<size_t>(src_row) * vocab + c, fp32) : -INFINITY;
+        v[e] = c < vocab ? load_logit<T>(logits, static_cast<size_t>(row) * ld + (c - chunk0 * kChunk), fp32) : -INFINITY;
         mx = fmaxf(mx, v[e]);
     }
     __shared__ float red_f[kGrowThreads / 32];
@@ -90,8 +98,8 @@ __global__ void __launch_bounds__(kGrowThreads) grow_phase_a(const void* logits,
     if (tid == 0) {
         float t = 0.f;
         for (int w = 0; w < kGrowThreads / 32; ++w) t += red_f[w];
-        ws_max[row * n_chunks + chunk] = cmax;
-        ws_sum[row * n_chunks + chunk] = t;
+        blk[kBlkMax + row] = cmax;
+        blk[kBlkSum + row] = t;
     }
     // local top-k: k rounds of block arg-max (value desc, index asc)
     for (int it = 0; it < k; ++it) {
@@ -118,9 +126,8 @@ __global__ void __launch_bounds__(kGrowThreads) grow_phase_a(const void* logits,
                 if (red_f[w] > fv || (red_f[w] == fv && red_i[w] < fi)) { fv = red_f[w]; fi = red_i[w]; }
             bc_f = fv;
             bc_i = fi;
-            const size_t o = (static_cast<size_t>(row) * n_chunks + chunk) * k + it;
-            ws_val[o] = fv;
-            ws_idx[o] = fi;
+            blk[kBlkVal + row * LS_MAX_TOPK + it] = fv;
+            reinterpret_cast<int32_t*>(blk)[kBlkIdx + row * LS_MAX_TOPK + it] = fi;
         }
         __syncthreads();
         const int win = bc_i;
@@ -133,11 +140,9 @@ __global__ void __launch_bounds__(kGrowThreads) grow_phase_a(const void* logits,
 // Phase B (one CTA) + tree state update.  Phase A left, per (row, chunk), the chunk's top-k in descending order,
 // so the row-level and then the global top-k are k-way merges: one warp per row with the chunk lists spread over
 // its lanes, then one warp over the rows.  Every step is a warp arg-max over list heads - no scans.
-constexpr int kMaxRowsB = 32;
 constexpr int kMaxChunksPerLane = 8;      // vocab <= 32 * 8 * 2048 = 524288
 __global__ void __launch_bounds__(1024) grow_phase_b(ls_tree_state s, int vocab, int n_chunks, int k, int level,
-                                                     int level_begin, int n_rows, int n_new, const float* ws_max,
-                                                     const float* ws_sum, float* ws_val, const int32_t* ws_idx) {
+                                                     int level_begin, int n_rows, int n_new, const float* ws) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ float row_val[kMaxRowsB][LS_MAX_TOPK];
     __shared__ int row_idx[kMaxRowsB][LS_MAX_TOPK];
@@ -147,15 +152,19 @@ __global__ void __launch_bounds__(1024) grow_phase_b(ls_tree_state s, int vocab,
         const int row = warp;
         // log-normaliser of the row from the per-chunk (max, sum exp)
         float mx = -INFINITY;
-        for (int c = lane; c < n_chunks; c += 32) mx = fmaxf(mx, ws_max[row * n_chunks + c]);
+        for (int c = lane; c < n_chunks; c += 32) mx = fmaxf(mx, ws[static_cast<size_t>(c) * kBlkWords + kBlkMax + row]);
         mx = warp_max(mx);
         float sm = 0.f;
-        for (int c = lane; c < n_chunks; c += 32) sm += ws_sum[row * n_chunks + c] * expf(ws_max[row * n_chunks + c] - mx);
+        for (int c = lane; c < n_chunks; c += 32) {
+            const float cm = ws[static_cast<size_t>(c) * kBlkWords + kBlkMax + row];
+            // a chunk behind the end of the vocabulary (padding of the last rank's slice) holds max = -inf, sum = 0
+            sm += cm == -INFINITY ? 0.f : ws[static_cast<size_t>(c) * kBlkWords + kBlkSum + row] * expf(cm - mx);
+        }
         sm = warp_sum(sm);
         const float logsum = logf(sm);
         const float hist = level == 0 ? 0.f : s.scores[level_begin + row];
-        const float* cv = ws_val + static_cast<size_t>(row) * n_chunks * k;
-        const int32_t* ci = ws_idx + static_cast<size_t>(row) * n_chunks * k;
+        const float* cv = ws + kBlkVal + row * LS_MAX_TOPK;                                  // + chunk * kBlkWords + position
+        const int32_t* ci = reinterpret_cast<const int32_t*>(ws) + kBlkIdx + row * LS_MAX_TOPK;
         int ptr[kMaxChunksPerLane];
 #pragma unroll
         for (int q = 0; q < kMaxChunksPerLane; ++q) ptr[q] = 0;
@@ -166,8 +175,8 @@ __global__ void __launch_bounds__(1024) grow_phase_b(ls_tree_state s, int vocab,
             for (int q = 0; q < kMaxChunksPerLane; ++q) {
                 const int c = lane + q * 32;
                 if (c < n_chunks && ptr[q] < k) {
-                    const float x = cv[c * k + ptr[q]];
-                    const int id = ci[c * k + ptr[q]];
+                    const float x = cv[static_cast<size_t>(c) * kBlkWords + ptr[q]];
+                    const int id = ci[static_cast<size_t>(c) * kBlkWords + ptr[q]];
                     if (x > bv || (x == bv && id < bi)) { bv = x; bi = id; bq = q; }
                 }
             }
@@ -440,6 +449,50 @@ __global__ void pack_mask_kernel(const int64_t* dense, int rows, int cols, int64
     for (int w = 0; w < W; ++w) bits[r * W + w] = b[w];
 }
 
+// Vocab-sharded argmax: every rank reduces its vocabulary slice to (value, GLOBAL index) per row; after the exchange the
+// candidates of all ranks are merged by (value desc, index asc) - the order argmax_rows_kernel itself uses.
+template <typename T>
+__global__ void __launch_bounds__(1024) argmax_rows_partial_kernel(const void* logits, int fp32, int vocab_local, int64_t ld,
+                                                                   int vocab_begin, int64_t* out_pairs) {
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float bv = -INFINITY;
+    int bi = INT_MAX;
+    const size_t base = static_cast<size_t>(row) * ld;
+    for (int c = tid; c < vocab_local; c += blockDim.x) {
+        const float x = load_logit<T>(logits, base + c, fp32);
+        if (x > bv) { bv = x; bi = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    __shared__ float rv[32];
+    __shared__ int ri[32];
+    if (lane == 0) { rv[warp] = bv; ri[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < (blockDim.x >> 5); ++w)
+            if (rv[w] > bv || (rv[w] == bv && ri[w] < bi)) { bv = rv[w]; bi = ri[w]; }
+        out_pairs[2 * row] = static_cast<int64_t>(__float_as_uint(bv));
+        out_pairs[2 * row + 1] = bi == INT_MAX ? -1 : static_cast<int64_t>(bi) + vocab_begin;
+    }
+}
+
+__global__ void argmax_merge_kernel(const int64_t* pairs, int world, int rows, int64_t* out) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    float bv = -INFINITY;
+    int64_t bi = -1;
+    for (int r = 0; r < world; ++r) {
+        const float v = __uint_as_float(static_cast<uint32_t>(pairs[(static_cast<size_t>(r) * rows + row) * 2]));
+        const int64_t i = pairs[(static_cast<size_t>(r) * rows + row) * 2 + 1];
+        if (i >= 0 && (bi < 0 || v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+    }
+    out[row] = bi < 0 ? 0 : bi;
+}
+
 static int check_state(const ls_tree_state* s) {
     LS_REQUIRE(s != nullptr, "tree state is null");
     LS_REQUIRE(s->fseq >= 2 && s->fseq <= 64 * W, "fseq %d out of range [2,%d]", s->fseq, 64 * W);
@@ -461,45 +514,60 @@ extern "C" int ls_round_begin(const ls_tree_state* s, void* stream) {
     return check_launch("ls_round_begin");
 }
 
+extern "C" int64_t ls_grow_chunk_bytes(void) { return static_cast<int64_t>(ls::kBlkWords) * 4; }
+
 extern "C" int64_t ls_grow_workspace_bytes(int32_t max_rows, int32_t vocab) {
+    (void)max_rows;                                   // blocks have the kernels' fixed row capacity
     const int64_t n_chunks = (vocab + ls::kChunk - 1) / ls::kChunk;
-    return max_rows * n_chunks * (2 + 2 * LS_MAX_TOPK) * 4 + 256;
+    return (n_chunks + LS_MAX_PEERS) * ls_grow_chunk_bytes() + 256;      // + padding of the last rank's slice when sharded
 }
 
-extern "C" int ls_tree_grow(const ls_tree_state* s, const void* logits, int32_t logits_fp32, int32_t dtype,
-                            int32_t vocab, int32_t level, int32_t level_begin, int32_t level_end, int32_t n_new,
-                            void* workspace, void* stream) {
+extern "C" int ls_tree_grow_partial(const void* logits, int32_t logits_fp32, int32_t dtype, int32_t rows, int64_t ld,
+                                    int32_t vocab, int32_t chunk0, int32_t n_chunks_local, int32_t n_new, void* ws_slice,
+                                    void* stream) {
+    using namespace ls;
+    LS_REQUIRE(logits && ws_slice, "ls_tree_grow_partial: null logits/workspace");
+    LS_REQUIRE(n_new >= 1 && n_new <= LS_MAX_TOPK, "ls_tree_grow_partial: n_new %d out of range [1,%d]", n_new, LS_MAX_TOPK);
+    LS_REQUIRE(rows >= 1 && rows <= kMaxRowsB, "ls_tree_grow_partial: %d rows out of range [1,%d]", rows, kMaxRowsB);
+    LS_REQUIRE(chunk0 >= 0 && n_chunks_local >= 1 && ld >= 0, "ls_tree_grow_partial: bad slice");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid(n_chunks_local, rows);
+    if (dtype == LS_F16)
+        grow_phase_a<__half><<<grid, kGrowThreads, 0, st>>>(logits, logits_fp32, vocab, ld, chunk0, n_new, static_cast<float*>(ws_slice));
+    else
+        grow_phase_a<__nv_bfloat16><<<grid, kGrowThreads, 0, st>>>(logits, logits_fp32, vocab, ld, chunk0, n_new,
+                                                                   static_cast<float*>(ws_slice));
+    return check_launch("ls_tree_grow_partial");
+}
+
+extern "C" int ls_tree_grow_finish(const ls_tree_state* s, int32_t vocab, int32_t n_chunks, int32_t level,
+                                   int32_t level_begin, int32_t level_end, int32_t n_new, const void* workspace,
+                                   void* stream) {
     using namespace ls;
     int rc = check_state(s);
     if (rc) return rc;
-    LS_REQUIRE(logits && workspace, "ls_tree_grow: null logits/workspace");
+    LS_REQUIRE(workspace, "ls_tree_grow_finish: null workspace");
     LS_REQUIRE(n_new >= 1 && n_new <= LS_MAX_TOPK, "ls_tree_grow: n_new %d out of range [1,%d]", n_new, LS_MAX_TOPK);
     const int n_rows = level == 0 ? 1 : level_end - level_begin;
     LS_REQUIRE(n_rows >= 1 && n_rows <= kMaxRowsB, "ls_tree_grow: level width %d out of range [1,%d]", n_rows, kMaxRowsB);
     LS_REQUIRE(level >= 0 && level < s->gamma, "ls_tree_grow: level %d out of range", level);
     LS_REQUIRE(vocab >= n_new, "ls_tree_grow: vocab smaller than n_new");
-    LS_REQUIRE((vocab + kChunk - 1) / kChunk <= 32 * kMaxChunksPerLane, "ls_tree_grow: vocab %d too large", vocab);
+    LS_REQUIRE(n_chunks >= 1 && n_chunks <= 32 * kMaxChunksPerLane, "ls_tree_grow: vocab %d too large (%d chunks)", vocab, n_chunks);
     const int new_begin = level == 0 ? 1 : level_end;
     LS_REQUIRE(new_begin + n_new <= s->fseq, "ls_tree_grow: level overflows fseq");
-    const int n_chunks = (vocab + kChunk - 1) / kChunk;
-    float* ws_max = static_cast<float*>(workspace);
-    float* ws_sum = ws_max + static_cast<size_t>(n_rows) * n_chunks;
-    float* ws_val = ws_sum + static_cast<size_t>(n_rows) * n_chunks;
-    int32_t* ws_idx = reinterpret_cast<int32_t*>(ws_val + static_cast<size_t>(n_rows) * n_chunks * n_new);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    dim3 grid(n_chunks, n_rows);
-    const int32_t* row_sel = nullptr;   // level 0: the caller passes the single row acc_num-1 (ls_gather_rows)
-    if (dtype == LS_F16)
-        grow_phase_a<__half><<<grid, kGrowThreads, 0, st>>>(logits, logits_fp32, vocab, n_chunks, n_new, row_sel, ws_max,
-                                                            ws_sum, ws_val, ws_idx);
-    else
-        grow_phase_a<__nv_bfloat16><<<grid, kGrowThreads, 0, st>>>(logits, logits_fp32, vocab, n_chunks, n_new, row_sel,
-                                                                   ws_max, ws_sum, ws_val, ws_idx);
-    rc = check_launch("ls_tree_grow/a");
+    grow_phase_b<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(*s, vocab, n_chunks, n_new, level, level_begin, n_rows, n_new,
+                                                                    static_cast<const float*>(workspace));
+    return check_launch("ls_tree_grow_finish");
+}
+
+extern "C" int ls_tree_grow(const ls_tree_state* s, const void* logits, int32_t logits_fp32, int32_t dtype,
+                            int32_t vocab, int32_t level, int32_t level_begin, int32_t level_end, int32_t n_new,
+                            void* workspace, void* stream) {
+    const int n_rows = level == 0 ? 1 : level_end - level_begin;   // level 0: the caller passes the single row acc_num-1
+    const int n_chunks = (vocab + ls::kChunk - 1) / ls::kChunk;
+    int rc = ls_tree_grow_partial(logits, logits_fp32, dtype, n_rows, vocab, vocab, 0, n_chunks, n_new, workspace, stream);
     if (rc) return rc;
-    grow_phase_b<<<1, 1024, 0, st>>>(*s, vocab, n_chunks, n_new, level, level_begin, n_rows, n_new, ws_max, ws_sum, ws_val,
-                                     ws_idx);
-    return check_launch("ls_tree_grow/b");
+    return ls_tree_grow_finish(s, vocab, n_chunks, level, level_begin, level_end, n_new, workspace, stream);
 }
 
 extern "C" int ls_build_verify(const ls_tree_state* s, void* stream) {
@@ -549,4 +617,23 @@ extern "C" int ls_pack_mask(const int64_t* dense, int32_t rows, int32_t cols, in
     LS_REQUIRE(dense && bits && rows >= 1 && cols >= 1 && cols <= 64 * W, "ls_pack_mask: bad arguments (cols <= %d)", 64 * W);
     pack_mask_kernel<<<(rows + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(dense, rows, cols, row_stride, bits);
     return check_launch("ls_pack_mask");
+}
+
+extern "C" int ls_argmax_rows_partial(const void* logits, int32_t logits_fp32, int32_t dtype, int32_t rows, int32_t vocab_local,
+                                      int64_t ld, int32_t vocab_begin, int64_t* out_pairs, void* stream) {
+    using namespace ls;
+    LS_REQUIRE(logits && out_pairs && rows >= 1 && vocab_local >= 0, "ls_argmax_rows_partial: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == LS_F16)
+        argmax_rows_partial_kernel<__half><<<rows, 1024, 0, st>>>(logits, logits_fp32, vocab_local, ld, vocab_begin, out_pairs);
+    else
+        argmax_rows_partial_kernel<__nv_bfloat16><<<rows, 1024, 0, st>>>(logits, logits_fp32, vocab_local, ld, vocab_begin, out_pairs);
+    return check_launch("ls_argmax_rows_partial");
+}
+
+extern "C" int ls_argmax_merge(const int64_t* pairs, int32_t world, int32_t rows, int64_t* out, void* stream) {
+    using namespace ls;
+    LS_REQUIRE(pairs && out && world >= 1 && rows >= 1, "ls_argmax_merge: bad arguments");
+    argmax_merge_kernel<<<(rows + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(pairs, world, rows, out);
+    return check_launch("ls_argmax_merge");
 }

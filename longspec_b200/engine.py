@@ -309,6 +309,22 @@ class Engine:
             self.send_o = torch.empty(d.kv_heads * rows_max * 128, dtype=torch.float32, device=dev)
             self.send_lse = torch.empty(d.kv_heads * rows_max, dtype=torch.float32, device=dev)
         self.grow_ws = torch.empty(int(_lib.load().ls_grow_workspace_bytes(32, d.vocab)), dtype=torch.uint8, device=dev)
+        # Vocab-sharded lm_head (multi-GPU): the 6 lm_head GEMMs of a round read 6 x V x d weights that every rank would
+        # otherwise stream in full (6.3 GB of the replicated 22.9 GB per round for Llama-3-8B).  Rank r takes a
+        # chunk-aligned slice of the vocabulary (chunk = 2048 ids); the per-chunk reductions are all-gathered.
+        self.vshard = None
+        if world > 1 and os.environ.get("LONGSPEC_VOCAB_SHARD", "1") != "0":
+            n_chunks = (d.vocab + 2047) // 2048
+            cpr = (n_chunks + world - 1) // world                      # chunks per rank (the last slices may be short or empty)
+            c0 = sh.rank * cpr
+            v0, v1 = min(c0 * 2048, d.vocab), min((c0 + cpr) * 2048, d.vocab)
+            cb = int(_lib.load().ls_grow_chunk_bytes())
+            self.vshard = dict(cpr=cpr, c0=c0, v0=v0, v1=v1, n_chunks=cpr * world, chunk_bytes=cb,
+                               send=torch.empty(cpr * cb, dtype=torch.uint8, device=dev),
+                               pairs_send=torch.empty(self.fseq * 2, dtype=torch.int64, device=dev),
+                               pairs_all=torch.empty(world * self.fseq * 2, dtype=torch.int64, device=dev),
+                               head=self.w.lm_head[v0:v1] if v1 > v0 else None,
+                               dummy=torch.zeros(8, dtype=self.dtype, device=dev))
         self.descs = []                                # keep ctypes structs alive
 
     # ------------------------------------------------------------------ kernels
@@ -439,9 +455,20 @@ class Engine:
                                        self.n_split_verify, self.q_v, st["veri_bits"], 0)
         hn = self._norm(h, delta, self.w.norm)
         rows = self._gather(hn, st["logit_rows"], self.fseq)
-        logits = F.linear(rows, self.w.lm_head)
-        _lib.call("ls_argmax_rows", _ptr(logits), 0, self.code, self.fseq, self.dims.vocab, _ptr(st["llm_pred"]), _stream())
-        self.launches += 1
+        vs = self.vshard
+        if vs is None:
+            logits = F.linear(rows, self.w.lm_head)
+            _lib.call("ls_argmax_rows", _ptr(logits), 0, self.code, self.fseq, self.dims.vocab, _ptr(st["llm_pred"]), _stream())
+            self.launches += 1
+            return st["llm_pred"]
+        # vocab-sharded: local (value, global index) per row, all-gather, merge by (value desc, index asc)
+        import torch.distributed as dist
+        vloc = vs["v1"] - vs["v0"]
+        logits = F.linear(rows, vs["head"]) if vloc > 0 else vs["dummy"]
+        _lib.call("ls_argmax_rows_partial", _ptr(logits), 0, self.code, self.fseq, vloc, vloc, vs["v0"], _ptr(vs["pairs_send"]), _stream())
+        dist.all_gather_into_tensor(vs["pairs_all"], vs["pairs_send"], group=self.group)
+        _lib.call("ls_argmax_merge", _ptr(vs["pairs_all"]), self.shard.world, self.fseq, _ptr(st["llm_pred"]), _stream())
+        self.launches += 2
         return st["llm_pred"]
 
     def decode_one(self, ids, pos, out_tok):
@@ -503,10 +530,25 @@ class Engine:
         # --- lm_head + fused log-softmax / cumulative score / top-k / mask bookkeeping
         if level == 0:
             h = self._gather(h, st["aux"][1:2], 1)
-        logits = F.linear(h, self.w.lm_head)
         lo, hi = (0, 1) if level == 0 else (self.offs[level - 1], self.offs[level])
-        _lib.call("ls_tree_grow", C.byref(self.ts), _ptr(logits), 0, self.code, d.vocab, level, lo, hi,
-                  self.tree_shape[level], _ptr(self.grow_ws), _stream())
+        vs = self.vshard
+        if vs is None:
+            logits = F.linear(h, self.w.lm_head)
+            _lib.call("ls_tree_grow", C.byref(self.ts), _ptr(logits), 0, self.code, d.vocab, level, lo, hi,
+                      self.tree_shape[level], _ptr(self.grow_ws), _stream())
+            self.launches += 2
+            return
+        # vocab-sharded: per-chunk (max, sum exp, top-k) of this rank's slice, all-gather of the chunk blocks, then the
+        # same merges + tree update on every rank (identical inputs -> identical trees)
+        import torch.distributed as dist
+        vloc = vs["v1"] - vs["v0"]
+        n_rows = h.shape[0]
+        logits = F.linear(h, vs["head"]) if vloc > 0 else vs["dummy"]
+        _lib.call("ls_tree_grow_partial", _ptr(logits), 0, self.code, n_rows, vloc, d.vocab, vs["c0"], vs["cpr"],
+                  self.tree_shape[level], _ptr(vs["send"]), _stream())
+        dist.all_gather_into_tensor(self.grow_ws[:vs["n_chunks"] * vs["chunk_bytes"]], vs["send"], group=self.group)
+        _lib.call("ls_tree_grow_finish", C.byref(self.ts), d.vocab, vs["n_chunks"], level, lo, hi, self.tree_shape[level],
+                  _ptr(self.grow_ws), _stream())
         self.launches += 2
 
     # ------------------------------------------------------------------ one decode round

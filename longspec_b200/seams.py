@@ -105,8 +105,11 @@ def tree_verification(input_ids, output_ids, tree_mask, cache_lens, non_leaf_len
     cache_len = int(cache_lens.reshape(-1)[0])
     with torch.cuda.device(dev):
         # a one-level tree state of the right size; prompt_len = cache_len so that the accepted ids land at output slot 1..
-        # (a chain of fseq - 1 levels: acc_ids is sized by the depth, and the depth of the caller's tree is not known here)
-        st, ts = alloc_tree_state(dev, [1] * max(fseq - 1, 1), cache_len, fseq + 8)
+        # (a chain-shaped state: acc_ids is sized by the depth, and the depth of the caller's tree is not known here;
+        # the kernels take at most 16 levels; a real tree is never deeper than gamma + 1 <= 17 nodes)
+        n = max(fseq - 1, 1)
+        shape = [1] * n if n <= 16 else [1] * 15 + [n - 15]
+        st, ts = alloc_tree_state(dev, shape, cache_len, fseq + 8)
         ts.fseq = fseq
         tm = (tree_mask[0] != 0)
         dense = tm.to(torch.int64).contiguous()

@@ -163,3 +163,79 @@ def test_pack_mask_matches_host_packing():
     _lib.call("ls_pack_mask", _ptr(md), 74, 150, md.stride(0), _ptr(bits), _stream())
     torch.cuda.synchronize()
     assert torch.equal(bits.cpu(), pack_bits(m))
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("logit_kind", ["fp32", "bf16"])
+def test_vocab_sharded_tree_growth_equals_unsharded(world, logit_kind):
+    """ls_tree_grow_partial per vocabulary slice (as each rank of a vocab-sharded lm_head runs it) + ls_tree_grow_finish on
+    the concatenated chunk blocks == ls_tree_grow on the whole vocabulary, bit for bit, incl. the tie rule (bf16 logits
+    are full of exact ties) and slices that are short or empty (V = 5003 = 3 chunks of 2048 over up to 8 ranks)."""
+    from longspec_b200 import _lib
+    from longspec_b200.engine import _ptr, _stream
+    shape, V = [4, 16, 16, 16, 16], 5003
+    offs = OT.level_offsets(shape)
+    fp32 = logit_kind == "fp32"
+    lib = _lib.load()
+    cb = int(lib.ls_grow_chunk_bytes())
+    n_chunks = (V + 2047) // 2048
+    cpr = (n_chunks + world - 1) // world
+    results = []
+    for sharded in (False, True):
+        dev, st, ts = _setup(shape)
+        st["acc_ids"][:3] = torch.tensor([11, 22, 33])
+        st["scalars"][:4] = torch.tensor([500, 503, 498, 3], dtype=torch.int32)
+        ws = torch.empty(int(lib.ls_grow_workspace_bytes(32, V)), dtype=torch.uint8, device=dev)
+        _lib.call("ls_round_begin", C.byref(ts), _stream())
+        gen = torch.Generator().manual_seed(7)
+        for lv in range(len(shape)):
+            M = 1 if lv == 0 else shape[lv - 1]
+            logits = torch.randn(M, V, generator=gen) * 3
+            if not fp32:
+                logits = logits.to(torch.bfloat16)
+            lo, hi = (0, 1) if lv == 0 else (offs[lv - 1], offs[lv])
+            if not sharded:
+                dl = logits.to(dev)
+                _lib.call("ls_tree_grow", C.byref(ts), _ptr(dl), int(fp32), _lib.LS_BF16, V, lv, lo, hi, shape[lv], _ptr(ws), _stream())
+            else:
+                ws.fill_(0x7f)                                     # stale garbage must not leak into the merge
+                keep = []
+                for r in range(world):
+                    c0 = r * cpr
+                    v0, v1 = min(c0 * 2048, V), min((c0 + cpr) * 2048, V)
+                    loc = logits[:, v0:v1].contiguous().to(dev) if v1 > v0 else torch.zeros(8, dtype=logits.dtype, device=dev)
+                    keep.append(loc)
+                    _lib.call("ls_tree_grow_partial", _ptr(loc), int(fp32), _lib.LS_BF16, M, v1 - v0, V, c0, cpr, shape[lv],
+                              _ptr(ws[r * cpr * cb:]), _stream())
+                _lib.call("ls_tree_grow_finish", C.byref(ts), V, cpr * world, lv, lo, hi, shape[lv], _ptr(ws), _stream())
+            torch.cuda.synchronize()
+        results.append({k: st[k].clone().cpu() for k in ("all_spec", "scores", "parent", "depth", "tree_bits", "step_ids", "step_pos")})
+    for k in results[0]:
+        assert torch.equal(results[0][k], results[1][k]), f"{k} differs between the sharded and the unsharded growth"
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_vocab_sharded_argmax_equals_unsharded(world):
+    from longspec_b200 import _lib
+    from longspec_b200.engine import _ptr, _stream
+    dev = torch.device("cuda:0")
+    rows, V = 69, 5003
+    logits = (torch.randn(rows, V, generator=torch.Generator().manual_seed(3)) * 2).to(torch.bfloat16)   # ties galore
+    logits[5, 4000] = logits[5, 17] = 30.0                          # an exact tie across slices: the lower index wins
+    dl = logits.to(dev)
+    ref = torch.zeros(rows, dtype=torch.int64, device=dev)
+    _lib.call("ls_argmax_rows", _ptr(dl), 0, _lib.LS_BF16, rows, V, _ptr(ref), _stream())
+    n_chunks = (V + 2047) // 2048
+    cpr = (n_chunks + world - 1) // world
+    pairs = torch.zeros(world * rows * 2, dtype=torch.int64, device=dev)
+    keep = []
+    for r in range(world):
+        v0, v1 = min(r * cpr * 2048, V), min((r + 1) * cpr * 2048, V)
+        loc = logits[:, v0:v1].contiguous().to(dev) if v1 > v0 else torch.zeros(8, dtype=torch.bfloat16, device=dev)
+        keep.append(loc)
+        _lib.call("ls_argmax_rows_partial", _ptr(loc), 0, _lib.LS_BF16, rows, v1 - v0, v1 - v0, v0, _ptr(pairs[r * rows * 2:]), _stream())
+    out = torch.zeros(rows, dtype=torch.int64, device=dev)
+    _lib.call("ls_argmax_merge", _ptr(pairs), world, rows, _ptr(out), _stream())
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref) and int(out[5]) == 17
+    assert torch.equal(out.cpu(), logits.float().argmax(-1)) or True   # torch's tie order is unspecified; ours is first index
