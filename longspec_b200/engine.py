@@ -281,7 +281,7 @@ class Engine:
         world = sh.world
         max_parts = max(self.n_split_verify, self.n_split_cross, self.n_split_one)
         max_parts = max(max_parts, self.n_split_self)
-        rows_max = self.q_v * G
+        rows_max = max(self.q_v, max(1, 256 // G)) * G          # verify rows, or a prefill block of 256 // G query tokens
         self.part_o = torch.empty(max_parts * d.kv_heads * rows_max * 128, dtype=torch.float32, device=dev)
         self.part_lse = torch.empty(max_parts * d.kv_heads * rows_max, dtype=torch.float32, device=dev)
         # multi-GPU exchange blocks: ONE locally reduced (O, lse) partial per rank and attention call
@@ -568,11 +568,21 @@ class Engine:
         self.launches += 3
 
     # ------------------------------------------------------------------ prefill (state set-up, untimed)
+    def _prefill_splits(self, end):
+        """Split-KV slots for a prefill block whose causal context ends at token `end` (this rank's share of it)."""
+        sh, d = self.shard, self.dims
+        hi = end if sh.end < 0 else min(sh.end, end)
+        tiles128 = max((max(hi - sh.begin, 0) + 127) // 128, 1)
+        return int(max(1, min(self.sms // d.kv_heads, (tiles128 + 3) // 4)))
+
     def prefill(self, input_ids, chunk=8192):
-        """Target + draft prefill.  Uses torch SDPA for the O(P^2) causal attention: prefill is
-        state set-up outside the timed decode path (llama_glide.py:954-975 run before the timer at 993)
-        and outside this round's kernel scope.  Fills the paged pools
-        (this rank's shard only) and returns the last position's final hidden state [1, hidden]."""
+        """Target + draft prefill on the package's own kernels (llama.py:199-226, llama_glide.py:206-233,954-975; state
+        set-up before the reference's timer at llama_glide.py:993).  The O(P^2) causal attention runs on the SAME
+        tcgen05 split-KV kernel as the decode loop: the layer's K/V go into the paged pool first, then every block of
+        256 // G query tokens attends to the pool with `causal` set and kv_len = the block's end.  With the prefix KV
+        sharded over several GPUs each rank attends only to its own shard and the per-block partials are merged
+        through the same exchange as in decoding - the quadratic part of the prefill is divided by the world size
+        (the GEMMs stay replicated, like the weights).  Returns the last position's final hidden state [1, hidden]."""
         d, w, sh = self.dims, self.w, self.shard
         P = self.prompt_len                      # KV sizing, cache_len and the shard plan were made for prompt_length
         if input_ids.shape[1] < P:
@@ -580,6 +590,7 @@ class Engine:
         ids = input_ids[0, :P].to(self.device)
         pos = torch.arange(P, device=self.device, dtype=torch.int32)
         HD, KD = d.heads * 128, d.kv_heads * 128
+        G = d.heads // d.kv_heads
         h = w.embed[ids]
         one = torch.tensor([P], dtype=torch.int32, device=self.device)
         zero = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -593,8 +604,13 @@ class Engine:
         del xd, qkv
         lo = sh.begin
         hi = P if sh.end < 0 else min(sh.end, P)
+        Bq = max(1, 256 // G)                                        # query tokens per attention call (<= 256 packed rows)
+        n_blocks = (P + Bq - 1) // Bq
+        P_pad = n_blocks * Bq
+        ends = torch.tensor([min((b + 1) * Bq, P) for b in range(n_blocks)], dtype=torch.int32, device=self.device)
+        n_valid = torch.tensor([min(Bq, P - b * Bq) for b in range(n_blocks)], dtype=torch.int32, device=self.device)
         for li, L in enumerate(w.layers):
-            q = torch.empty(P, HD, dtype=self.dtype, device=self.device)
+            q = torch.zeros(P_pad, HD, dtype=self.dtype, device=self.device)
             k = torch.empty(P, KD, dtype=self.dtype, device=self.device)
             v = torch.empty(P, KD, dtype=self.dtype, device=self.device)
             for s in range(0, P, chunk):
@@ -606,14 +622,14 @@ class Engine:
                 q[s:e], k[s:e], v[s:e] = qkv[:, :HD], qkv[:, HD:HD + KD], qkv[:, HD + KD:]
             if hi > lo:
                 self.kv.write(li, k[lo:hi].view(-1, d.kv_heads, 128), v[lo:hi].view(-1, d.kv_heads, 128), 0)
-            G = d.heads // d.kv_heads
-            kx = k.view(P, d.kv_heads, 1, 128).expand(P, d.kv_heads, G, 128).reshape(1, P, d.heads, 128)
-            vx = v.view(P, d.kv_heads, 1, 128).expand(P, d.kv_heads, G, 128).reshape(1, P, d.heads, 128)
-            a = F.scaled_dot_product_attention(q.view(1, P, d.heads, 128).transpose(1, 2), kx.transpose(1, 2),
-                                               vx.transpose(1, 2), is_causal=True, scale=self.scale)
-            del kx, vx
-            a = a.transpose(1, 2).reshape(P, HD)
-            del q, k, v
+            del k, v
+            a = torch.empty(P_pad, HD, dtype=self.dtype, device=self.device)
+            for b in range(n_blocks):
+                s0 = b * Bq
+                self._attn(q[s0:s0 + Bq], a[s0:s0 + Bq], self.kv, li, ends[b:b + 1], n_valid[b:b + 1], Bq,
+                           self._prefill_splits(min(s0 + Bq, P)), causal=1)
+            self.descs.clear()
+            del q
             for s in range(0, P, chunk):
                 e = min(s + chunk, P)
                 hs = h[s:e]
