@@ -103,10 +103,19 @@ typedef struct ls_attn_desc {
     float scale;                /* softmax scale, 1/sqrt(128) */
     int64_t q_stride;           /* elements between consecutive query rows of `q` (0 = dense, n_heads * 128): lets the
                                    q slice of a fused QKV GEMM output be read in place */
+    uint32_t* fuse_sync;        /* NULL, or 2 * n_kv_heads zero-initialised counters: the tcgen05 path of ls_attn_partial
+                                   then ALSO merges the partial slots and writes `out` (what ls_attn_combine does) in its
+                                   tail - the CTAs of a kv head meet at a counter barrier and share the rows out - so the
+                                   caller skips ls_attn_combine.  Honoured only when the call runs on the tcgen05 kernel
+                                   with part_offset == 0, n_parts_total == n_splits and a grid that fits the device in
+                                   one wave (ls_attn_fuses_combine tells); ignored otherwise. */
 } ls_attn_desc;
 
 /* split-KV partial pass: writes (normalised O, LSE) per (split, kv head, row) into the workspace */
 int ls_attn_partial(const ls_attn_desc* d, void* stream);
+/* 1 if ls_attn_partial(d) will merge the slots and write d->out itself (d->fuse_sync set and the conditions above hold),
+ * 0 if the caller has to run ls_attn_combine, negative on a bad descriptor.  No GPU work. */
+int ls_attn_fuses_combine(const ls_attn_desc* d);
 /* the general mma.sync data path behind ls_attn_partial (kept callable for cross-checks) */
 int ls_attn_partial_mma(const ls_attn_desc* d, void* stream);
 /* the tcgen05/TMA data path alone: unmasked full 128-key tiles of the prefix into n_splits_tc slots (window < 0,

@@ -27,7 +27,7 @@ class AttnDesc(C.Structure):
         ("kv_len_bias", i32), ("q_rows", i32), ("n_heads", i32), ("n_kv_heads", i32), ("n_tail", i32),
         ("window", i32), ("causal", i32), ("dtype", i32), ("n_splits", i32), ("n_pages", i32),
         ("part_offset", i32), ("n_parts_total", i32), ("kv_shard_begin", i32), ("kv_shard_end", i32),
-        ("tail_owner", i32), ("scale", f32), ("q_stride", i64),
+        ("tail_owner", i32), ("scale", f32), ("q_stride", i64), ("fuse_sync", vp),
     ]
 
 
@@ -57,6 +57,7 @@ _SIGS = {
     "ls_last_error": (C.c_char_p, []),
     "ls_sm_count": (i32, []),
     "ls_attn_partial": (i32, [C.POINTER(AttnDesc), vp]),
+    "ls_attn_fuses_combine": (i32, [C.POINTER(AttnDesc)]),
     "ls_attn_partial_mma": (i32, [C.POINTER(AttnDesc), vp]),
     "ls_attn_partial_tc": (i32, [C.POINTER(AttnDesc), i32, vp]),
     "ls_attn_combine": (i32, [C.POINTER(AttnDesc), vp]),

@@ -34,13 +34,27 @@ extern "C" int ls_attn_partial_tc_fused(const ls_attn_desc* d, void* stream);
 // stream the long unmasked prefix and one more CTA handles the masked remainder (partial tile, causal rows,
 // tree-masked tail) in the same launch; everything else (the draft's 512-token window) stays on the general
 // mma.sync kernel.  LONGSPEC_ATTN=mma forces the general path, LONGSPEC_ATTN=tc+mma the unfused pair.
-extern "C" int ls_attn_partial(const ls_attn_desc* d, void* stream) {
+extern "C" int ls_attn_tc_fuses_combine(const ls_attn_desc* d);
+
+static int attn_mode() {
     static const int mode = []() {
         const char* e = getenv("LONGSPEC_ATTN");
         if (e && strcmp(e, "mma") == 0) return 1;
         if (e && strcmp(e, "tc+mma") == 0) return 2;
         return 0;
     }();
+    return mode;
+}
+
+extern "C" int ls_attn_fuses_combine(const ls_attn_desc* d) {
+    if (!d || d->n_kv_heads < 1) return LS_ERR_INVALID_ARG;
+    const int G = d->n_heads / d->n_kv_heads;
+    const bool tc = attn_mode() == 0 && d->window < 0 && d->q_rows * G <= 384 && d->n_pages > 0;
+    return tc ? ls_attn_tc_fuses_combine(d) : 0;
+}
+
+extern "C" int ls_attn_partial(const ls_attn_desc* d, void* stream) {
+    const int mode = attn_mode();
     const int force_mma = mode == 1;
     if (!d || d->n_kv_heads < 1) return ls_attn_partial_mma(d, stream);
     const int G = d->n_heads / d->n_kv_heads;

@@ -346,7 +346,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
     // tokens.  They come from a small table in shared memory and the softmax applies a per-row bit mask to them.
     SpecialTile* sp_tiles = reinterpret_cast<SpecialTile*>(smem + OFF_SPECIAL);
     int n_special = 0;
-    if (fuse) {
+    if (fuse & 1) {
         const int sb = d.kv_shard_begin;
         const int se = d.kv_shard_end < 0 ? INT_MAX : d.kv_shard_end;
         const int loc_end = max(min(kv_len, se) - sb, 0);
@@ -769,6 +769,59 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                     *reinterpret_cast<float4*>(d.part_o + part_base(empty_slot, rp) * 128 + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
+        // ---- fused combine (ls_attn_desc::fuse_sync): the CTAs of this kv head meet at a counter barrier, then share
+        // the head's rows out and merge the n_slots partial slots of each - what ls_attn_combine would do in a second
+        // launch.  The partials are L2-resident; they were written by other SMs, hence the .cg loads.  All CTAs of the
+        // grid are resident at once (the host only sets `fuse` when the grid fits the device in one wave), so the
+        // spin cannot starve a CTA that has yet to arrive.
+        if (fuse & 2) {
+            uint32_t* arrive = d.fuse_sync + kvh;
+            uint32_t* depart = d.fuse_sync + d.n_kv_heads + kvh;
+            __threadfence();
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (tid == 128) {
+                atomicAdd(arrive, 1u);
+                while (*reinterpret_cast<volatile uint32_t*>(arrive) < gridDim.x) { }
+                __threadfence();
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            const int sw = warp - 4;
+            T* out = reinterpret_cast<T*>(d.out);
+            const size_t pstride = static_cast<size_t>(d.n_kv_heads) * Rtot;       // rows between slots
+            for (int r = bx * 16 + sw; r < Rtot; r += gridDim.x * 16) {
+                const int i = r / G, g = r - i * G;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < n_q) {
+                    const size_t row0 = static_cast<size_t>(kvh) * Rtot + r;
+                    const float lse = lane < n_slots ? __ldcg(d.part_lse + lane * pstride + row0) : -INFINITY;   // n_slots <= 32
+                    const float mx = warp_max(lse);
+                    if (mx != -INFINITY) {
+                        const float w_mine = lse == -INFINITY ? 0.f : __expf(lse - mx);
+                        const float wsum = warp_sum(w_mine);
+                        const float* base = d.part_o + row0 * 128 + lane * 4;
+#pragma unroll 4
+                        for (int k = 0; k < n_slots; ++k) {
+                            const float w = __shfl_sync(0xffffffffu, w_mine, k);
+                            const float4 v = __ldcg(reinterpret_cast<const float4*>(base + k * pstride * 128));
+                            acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                            acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                        }
+                        const float inv = 1.f / wsum;
+                        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+                    }
+                }
+                uint2 pk;
+                pk.x = Num<T>::pack(acc.x, acc.y);
+                pk.y = Num<T>::pack(acc.z, acc.w);
+                *reinterpret_cast<uint2*>(out + (static_cast<size_t>(i) * d.n_heads + kvh * G + g) * 128 + lane * 4) = pk;
+            }
+            // the last CTA to leave resets the counters for the next launch (stream-ordered behind this one)
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (tid == 128 && atomicAdd(depart, 1u) == gridDim.x - 1) {
+                *arrive = 0;
+                *depart = 0;
+            }
+        }
         tc_fence_before();
     }
     __syncthreads();
@@ -838,6 +891,18 @@ static int get_map(const void* pool, long long rows, int dtype, CUtensorMap* out
 // rows, tree-masked tail) is appended to the tile sequence as special tiles and shared out with the rest.
 // Up to two row tiles: one CTA per (slot, kv head).  Three row tiles: two heavy CTAs per pair of slots plus
 // one light CTA (see the header comment): grid.x = n_slots + ceil(n_slots / 2).
+// Can this call merge its partial slots in the kernel's tail?  (tcgen05 path, all slots written by this launch and merged by
+// nobody else, <= 32 slots (one LSE per lane), and a grid that is resident in one wave: the kv-head barrier spins.)
+static bool tc_can_fuse_combine(const ls_attn_desc* d, int n_splits_tc) {
+    if (!d->fuse_sync || !d->out || d->part_offset != 0 || d->n_parts_total != n_splits_tc || n_splits_tc > 32) return false;
+    const int G = d->n_heads / d->n_kv_heads;
+    const int nrs = (d->q_rows * G + 127) / 128;
+    const int gx = nrs > ls::tc::NRL_MAX ? n_splits_tc + (n_splits_tc + 1) / 2 : n_splits_tc;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
+    return gx * d->n_kv_heads <= sms;
+}
+
 static int launch_tc(const ls_attn_desc* d, int n_splits_tc, int fuse_remainder, void* stream) {
     using namespace ls;
     using namespace ls::tc;
@@ -862,10 +927,11 @@ static int launch_tc(const ls_attn_desc* d, int n_splits_tc, int fuse_remainder,
     const int nrs = (d->q_rows * G + 127) / 128;
     dim3 grid(nrs > NRL_MAX ? n_splits_tc + (n_splits_tc + 1) / 2 : n_splits_tc, d->n_kv_heads);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int fuse = (fuse_remainder ? 1 : 0) | ((fuse_remainder && tc_can_fuse_combine(d, n_splits_tc)) ? 2 : 0);
     if (d->dtype == LS_F16)
-        attn_tc_kernel<__half><<<grid, THREADS, SMEM_BYTES, st>>>(*d, mk, mv, n_splits_tc, fuse_remainder);
+        attn_tc_kernel<__half><<<grid, THREADS, SMEM_BYTES, st>>>(*d, mk, mv, n_splits_tc, fuse);
     else
-        attn_tc_kernel<__nv_bfloat16><<<grid, THREADS, SMEM_BYTES, st>>>(*d, mk, mv, n_splits_tc, fuse_remainder);
+        attn_tc_kernel<__nv_bfloat16><<<grid, THREADS, SMEM_BYTES, st>>>(*d, mk, mv, n_splits_tc, fuse);
     return check_launch("ls_attn_partial_tc");
 }
 
@@ -885,3 +951,6 @@ extern "C" int ls_attn_partial_tc_fused(const ls_attn_desc* d, void* stream) {
     LS_REQUIRE(d && d->n_splits >= 1, "ls_attn_partial_tc_fused: needs n_splits >= 1");
     return launch_tc(d, d->n_splits, 1, stream);
 }
+
+// does ls_attn_partial_tc_fused(d) merge the slots itself?  (see ls_attn_desc::fuse_sync)
+extern "C" int ls_attn_tc_fuses_combine(const ls_attn_desc* d) { return tc_can_fuse_combine(d, d->n_splits) ? 1 : 0; }

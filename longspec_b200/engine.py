@@ -325,6 +325,13 @@ class Engine:
                                pairs_all=torch.empty(world * self.fseq * 2, dtype=torch.int64, device=dev),
                                head=self.w.lm_head[v0:v1] if v1 > v0 else None,
                                dummy=torch.zeros(8, dtype=self.dtype, device=dev))
+        # counters of the fused split-KV combine (ls_attn_desc::fuse_sync); single GPU only - sharded calls merge in the
+        # exchange kernels instead.  OFF by default: measured on B200 the fused tail costs what the separate 5 us combine
+        # launch costs (12.610 vs 12.603 ms per round at 128k, 6.680 vs 6.657 at 16k, profiles/r02_fused_combine_ab.txt) -
+        # the CTAs of a kv head wait for their slowest member at the barrier - so it only makes the attention launch
+        # longer.  LONGSPEC_FUSE_COMBINE=1 turns it on.
+        self.fuse_sync = torch.zeros(2 * d.kv_heads, dtype=torch.int32, device=dev) \
+            if world == 1 and os.environ.get("LONGSPEC_FUSE_COMBINE", "0") == "1" else None
         self.descs = []                                # keep ctypes structs alive
 
     # ------------------------------------------------------------------ kernels
@@ -346,6 +353,7 @@ class Engine:
         a.kv_shard_begin, a.kv_shard_end, a.tail_owner = sh.begin, sh.end, int(sh.owner)
         a.scale = self.scale
         a.q_stride = q.stride(0)             # the q slice of a fused QKV output is read in place
+        a.fuse_sync = _ptr(self.fuse_sync) if (sharded and self.fuse_sync is not None) else C.c_void_p(0)
         return a
 
     def _attn(self, q, out, pools, layer, kv_len_ptr, n_q_ptr, q_rows, n_splits, **kw):
@@ -362,6 +370,9 @@ class Engine:
             return
         if sharded and self.shard.world > 1:
             a = self._exchange_partials(a, q_rows)
+        elif _lib.load().ls_attn_fuses_combine(C.byref(a)) == 1:
+            self.launches += 1               # the attention kernel merged its slots and wrote `out` itself
+            return
         _lib.call("ls_attn_combine", C.byref(a), _stream())
         self.launches += 2
 

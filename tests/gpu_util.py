@@ -34,7 +34,7 @@ def paged_from_dense(K, V, dtype, device, shuffle=True):
 
 
 def run_attention(q, kv, kv_len, n_q, *, n_tail=0, tail_mask=None, window=-1, causal=0, n_splits=3,
-                  shard=(0, -1, 1), world_parts=None, entry="ls_attn_partial", layer=0):
+                  shard=(0, -1, 1), world_parts=None, entry="ls_attn_partial", layer=0, fuse=False):
     """q [q_rows][H][128] on the GPU.  Returns out [q_rows][H][128]."""
     device, dtype = q.device, q.dtype
     q_rows, H, _ = q.shape
@@ -62,7 +62,15 @@ def run_attention(q, kv, kv_len, n_q, *, n_tail=0, tail_mask=None, window=-1, ca
     a.part_offset, a.n_parts_total = 0, n_parts
     a.kv_shard_begin, a.kv_shard_end, a.tail_owner = shard
     a.scale = 1.0 / math.sqrt(128)
+    sync = None
+    if fuse:                                 # fused split-KV combine: the attention kernel writes `out` itself
+        sync = torch.zeros(2 * Hk, dtype=torch.int32, device=device)
+        a.fuse_sync = _ptr(sync)
+        assert _lib.load().ls_attn_fuses_combine(C.byref(a)) == 1, "this call was expected to fuse its combine"
     _lib.call(entry, C.byref(a), _stream())
-    _lib.call("ls_attn_combine", C.byref(a), _stream())
+    if not fuse:
+        _lib.call("ls_attn_combine", C.byref(a), _stream())
     torch.cuda.synchronize()
+    if fuse:
+        assert int(sync.abs().sum()) == 0, "the fused combine must leave its counters at zero for the next launch"
     return out, part_o, part_l

@@ -146,3 +146,31 @@ def test_more_slots_than_tiles_leaves_empty_ctas_harmless():
     ref, _ = flash_ref.attend(q.float(), K[:n0].float(), V[:n0].float())
     assert torch.isfinite(tc).all()
     torch.testing.assert_close(tc, ref, atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("H,Hk,n0,n_q,splits,n_tail,causal", [
+    (8, 2, 3000, 74, 12, 74, 0),      # three row tiles (trios) + tree-masked tail: the verify shape
+    (8, 2, 3000, 69, 12, 74, 0),      # fewer live rows than planned
+    (32, 8, 16384, 74, 12, 74, 0),    # the headline head geometry: 144 CTAs
+    (8, 2, 2048, 16, 4, 0, 1),        # two-row-tile plan, causal (draft cross attention, step 0)
+    (8, 2, 5000, 64, 9, 0, 1),        # a prefill block: 256 packed rows, causal
+    (4, 4, 700, 74, 3, 74, 0),        # MHA, one row tile
+    (8, 2, 40, 74, 4, 74, 0),         # more slots than tiles: empty CTAs still take part in the barrier
+])
+def test_fused_combine_equals_partial_plus_combine(dtype, H, Hk, n0, n_q, splits, n_tail, causal):
+    """ls_attn_desc::fuse_sync: the attention kernel merges its split-KV slots in its own tail (kv-head counter barrier) -
+    bit-identical to ls_attn_partial + ls_attn_combine, twice in a row (the counters must reset themselves)."""
+    from gpu_util import paged_from_dense, run_attention
+    dev = torch.device("cuda:0")
+    q_rows = max(n_q, 74 if n_tail else n_q)
+    q = gen((q_rows, H, 128), 1, dtype).to(dev)
+    K = gen((n0 + q_rows + 9, Hk, 128), 2, dtype)
+    V = gen((n0 + q_rows + 9, Hk, 128), 3, dtype)
+    kv = paged_from_dense(K, V, dtype, dev)
+    mask = torch.tril(torch.ones(q_rows, n_tail, dtype=torch.int64)) if n_tail else None
+    kw = dict(n_tail=n_tail, tail_mask=mask, causal=causal, n_splits=splits)
+    ref, _, _ = run_attention(q, kv, n0, n_q, **kw)
+    for _ in range(2):
+        got, _, _ = run_attention(q, kv, n0, n_q, fuse=True, **kw)
+        assert torch.equal(got[:n_q], ref[:n_q])

@@ -26,7 +26,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_struct_layouts_match_the_header():
     """ctypes mirrors must have the header's field order/sizes (a mismatch corrupts every call)."""
     from longspec_b200._lib import AttnDesc, TreeState
-    assert ctypes.sizeof(AttnDesc) == 10 * 8 + 16 * 4 + 8
+    assert ctypes.sizeof(AttnDesc) == 10 * 8 + 16 * 4 + 8 + 8
     assert ctypes.sizeof(TreeState) == 21 * 8 + 4 * 4
     hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "longspec_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
