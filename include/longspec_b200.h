@@ -159,6 +159,12 @@ typedef struct ls_xchg {
 int ls_attn_reduce_push(const ls_attn_desc* d, const ls_xchg* x, void* stream);
 /* d->part_o / part_lse / n_parts_total are ignored: the kernel merges the `world` blocks of this rank's buffer */
 int ls_attn_combine_wait(const ls_attn_desc* d, const ls_xchg* x, void* stream);
+/* Generic small all-gather over the same buffer, flags and epoch (the chunk blocks / argmax pairs of a vocab-sharded
+ * lm_head): ls_peer_push copies `bytes` from `src` into slot `rank` of every rank's O region (parity = epoch & 1) and
+ * publishes the epoch; ls_peer_gather_wait spins until every source's flag shows it, copies the `world` slots (slot_bytes
+ * apart, rank order) to `dst` and advances the epoch.  bytes <= slot_bytes <= block_o * 4, multiples of 16. */
+int ls_peer_push(const void* src, int64_t bytes, int64_t slot_bytes, const ls_xchg* x, void* stream);
+int ls_peer_gather_wait(void* dst, int64_t bytes, int64_t slot_bytes, const ls_xchg* x, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * RoPE + KV append.  Replaces apply_rotary_pos_emb (llama.py:378, llama_glide.py:256,294) and

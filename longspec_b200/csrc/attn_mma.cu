@@ -526,6 +526,50 @@ __global__ void __launch_bounds__(256) attn_combine_wait_kernel(const ls_attn_de
     }
 }
 
+// Generic small all-gather over the exchange buffer (same flags / epoch / parity protocol as the attention blocks).
+__global__ void __launch_bounds__(256) peer_push_kernel(const uint4* __restrict__ src, int64_t n16, int64_t slot16, const ls_xchg x) {
+    const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(x.local_sync);
+    const int64_t slot = static_cast<int64_t>(epoch & 1) * x.world + x.rank;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n16; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const uint4 v = src[i];
+        for (int p = 0; p < x.world; ++p) reinterpret_cast<uint4*>(x.peer_o[p])[slot * slot16 + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t ticket = atomicAdd(x.local_sync + 1, 1u);
+        if (ticket == gridDim.x - 1) {
+            x.local_sync[1] = 0;
+            __threadfence_system();
+            for (int p = 0; p < x.world; ++p) st_release_sys(x.peer_flags[p] + x.rank, epoch + 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) peer_gather_wait_kernel(uint4* __restrict__ dst, int64_t n16, int64_t slot16, const ls_xchg x) {
+    const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(x.local_sync);
+    if (threadIdx.x < x.world) {
+        const uint32_t* flag = x.peer_flags[x.rank] + threadIdx.x;
+        while (static_cast<int32_t>(ld_acquire_sys(flag) - (epoch + 1)) < 0) { }
+    }
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(x.peer_o[x.rank]) + static_cast<int64_t>(epoch & 1) * x.world * slot16;
+    const int64_t total = static_cast<int64_t>(x.world) * n16;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = i / n16, o = i - r * n16;
+        dst[i] = __ldcg(src + r * slot16 + o);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t ticket = atomicAdd(x.local_sync + 2, 1u);
+        if (ticket == gridDim.x - 1) {
+            x.local_sync[2] = 0;
+            x.local_sync[0] = epoch + 1;
+        }
+    }
+}
+
 static int validate(const ls_attn_desc* d) {
     LS_REQUIRE(d != nullptr, "ls_attn: null descriptor");
     LS_REQUIRE(d->q && d->out && d->k_pool && d->v_pool && d->page_table && d->kv_len_ptr && d->n_q_ptr,
@@ -637,4 +681,35 @@ extern "C" int ls_attn_combine_wait(const ls_attn_desc* d, const ls_xchg* x, voi
     else
         attn_combine_wait_kernel<__nv_bfloat16><<<(warps + 7) / 8, 256, 0, st>>>(*d, *x);
     return check_launch("ls_attn_combine_wait");
+}
+
+static int validate_gather(const void* p, int64_t bytes, int64_t slot_bytes, const ls_xchg* x, const char* what) {
+    using namespace ls;
+    LS_REQUIRE(p && x && x->local_sync && x->world >= 1 && x->world <= LS_MAX_PEERS && x->rank >= 0 && x->rank < x->world,
+               "%s: bad arguments", what);
+    LS_REQUIRE(bytes > 0 && bytes % 16 == 0 && slot_bytes % 16 == 0 && bytes <= slot_bytes && slot_bytes <= x->block_o * 4,
+               "%s: %lld bytes / slots of %lld do not fit the exchange blocks (%lld bytes)", what, static_cast<long long>(bytes),
+               static_cast<long long>(slot_bytes), static_cast<long long>(x->block_o * 4));
+    for (int r = 0; r < x->world; ++r) LS_REQUIRE(x->peer_o[r] && x->peer_flags[r], "%s: null peer pointer (rank %d)", what, r);
+    return LS_OK;
+}
+
+extern "C" int ls_peer_push(const void* src, int64_t bytes, int64_t slot_bytes, const ls_xchg* x, void* stream) {
+    using namespace ls;
+    int rc = validate_gather(src, bytes, slot_bytes, x, "ls_peer_push");
+    if (rc) return rc;
+    const int64_t n16 = bytes / 16;
+    const int blocks = static_cast<int>(n16 / 256 + 1 < 32 ? n16 / 256 + 1 : 32);
+    peer_push_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(src), n16, slot_bytes / 16, *x);
+    return check_launch("ls_peer_push");
+}
+
+extern "C" int ls_peer_gather_wait(void* dst, int64_t bytes, int64_t slot_bytes, const ls_xchg* x, void* stream) {
+    using namespace ls;
+    int rc = validate_gather(dst, bytes, slot_bytes, x, "ls_peer_gather_wait");
+    if (rc) return rc;
+    const int64_t n16 = bytes / 16, total = n16 * x->world;
+    const int blocks = static_cast<int>(total / 256 + 1 < 32 ? total / 256 + 1 : 32);
+    peer_gather_wait_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uint4*>(dst), n16, slot_bytes / 16, *x);
+    return check_launch("ls_peer_gather_wait");
 }

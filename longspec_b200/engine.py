@@ -376,6 +376,20 @@ class Engine:
         _lib.call("ls_attn_combine", C.byref(a), _stream())
         self.launches += 2
 
+    def _gather_small(self, dst, src):
+        """All-gather of a small per-rank block (the vocab-sharded lm_head's chunk blocks / argmax pairs): over the peer
+        exchange buffer when there is one (no NCCL launch inside the round), else NCCL."""
+        if self.peer is not None:
+            nb = src.numel() * src.element_size()
+            slot = (nb + 15) // 16 * 16
+            if nb % 16 == 0 and slot <= self.peer.block_o * 4:
+                _lib.call("ls_peer_push", _ptr(src), nb, slot, self.peer.ref, _stream())
+                _lib.call("ls_peer_gather_wait", _ptr(dst), nb, slot, self.peer.ref, _stream())
+                self.launches += 2
+                return
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(dst, src, group=self.group)
+
     def _exchange_partials(self, a, q_rows):
         """Sequence-sharded prefix (option A with a deterministic merge order): every rank
         reduces its own split-KV slots to ONE normalised (O, lse) block (ls_attn_reduce), one NCCL all-gather makes
@@ -477,7 +491,7 @@ class Engine:
         vloc = vs["v1"] - vs["v0"]
         logits = F.linear(rows, vs["head"]) if vloc > 0 else vs["dummy"]
         _lib.call("ls_argmax_rows_partial", _ptr(logits), 0, self.code, self.fseq, vloc, vloc, vs["v0"], _ptr(vs["pairs_send"]), _stream())
-        dist.all_gather_into_tensor(vs["pairs_all"], vs["pairs_send"], group=self.group)
+        self._gather_small(vs["pairs_all"], vs["pairs_send"])
         _lib.call("ls_argmax_merge", _ptr(vs["pairs_all"]), self.shard.world, self.fseq, _ptr(st["llm_pred"]), _stream())
         self.launches += 2
         return st["llm_pred"]
@@ -557,7 +571,7 @@ class Engine:
         logits = F.linear(h, vs["head"]) if vloc > 0 else vs["dummy"]
         _lib.call("ls_tree_grow_partial", _ptr(logits), 0, self.code, n_rows, vloc, d.vocab, vs["c0"], vs["cpr"],
                   self.tree_shape[level], _ptr(vs["send"]), _stream())
-        dist.all_gather_into_tensor(self.grow_ws[:vs["n_chunks"] * vs["chunk_bytes"]], vs["send"], group=self.group)
+        self._gather_small(self.grow_ws[:vs["n_chunks"] * vs["chunk_bytes"]], vs["send"])
         _lib.call("ls_tree_grow_finish", C.byref(self.ts), d.vocab, vs["n_chunks"], level, lo, hi, self.tree_shape[level],
                   _ptr(self.grow_ws), _stream())
         self.launches += 2
