@@ -313,7 +313,7 @@ def main():
 
     # ---------------- (B) device-resident: K graph replays between CUDA events ----------------
     eng, graph = m.eng, m.last_graph
-    exchange = eng.exchange
+    exchange, parallelism = eng.exchange, eng.parallelism
     assert graph is not None, "CUDA graph capture is required for the device-timed number"
     st = eng.st
     st["counters"][3] = 0                    # a set stop flag would turn the replayed rounds' acceptance into no-ops
@@ -426,7 +426,7 @@ def main():
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{MODEL} widths, random-init bf16 weights, {PROMPT}-token synthetic prompt, tree "
                                f"{' '.join(map(str, TREE))}, bsz 1, T=0",
-                   "parallelism": "single GPU" if world == 1 else f"prefix KV sequence-sharded over {world} GPUs, weights replicated",
+                   "parallelism": parallelism,
                    "exchange": exchange,
                    "l2": "inputs larger than L2: every round streams all weights and the whole KV cache (> 30 GB)",
                    "accepted_len_tau": tau, "draft_scale": DRAFT_SCALE},

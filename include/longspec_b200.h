@@ -165,6 +165,10 @@ int ls_attn_combine_wait(const ls_attn_desc* d, const ls_xchg* x, void* stream);
  * apart, rank order) to `dst` and advances the epoch.  bytes <= slot_bytes <= block_o * 4, multiples of 16. */
 int ls_peer_push(const void* src, int64_t bytes, int64_t slot_bytes, const ls_xchg* x, void* stream);
 int ls_peer_gather_wait(void* dst, int64_t bytes, int64_t slot_bytes, const ls_xchg* x, void* stream);
+/* All-reduce (sum) in the same scheme, for a tensor-parallel MLP (row-parallel down projection): after every rank has
+ * ls_peer_push'ed its fp32 partial [n_elems], ls_peer_sum_wait adds the `world` slots in rank order (fp32), rounds ONCE to
+ * `dtype` - like the single-GPU GEMM that accumulates in fp32 and rounds its output - and writes dst [n_elems]. */
+int ls_peer_sum_wait(void* dst, int64_t n_elems, int32_t dtype, int64_t slot_bytes, const ls_xchg* x, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * RoPE + KV append.  Replaces apply_rotary_pos_emb (llama.py:378, llama_glide.py:256,294) and

@@ -66,6 +66,7 @@ _SIGS = {
     "ls_attn_combine_wait": (i32, [C.POINTER(AttnDesc), C.POINTER(Xchg), vp]),
     "ls_peer_push": (i32, [vp, i64, i64, C.POINTER(Xchg), vp]),
     "ls_peer_gather_wait": (i32, [vp, i64, i64, C.POINTER(Xchg), vp]),
+    "ls_peer_sum_wait": (i32, [vp, i64, i32, i64, C.POINTER(Xchg), vp]),
     "ls_rope_append": (i32, [vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, i32, i32, i32, vp]),
     "ls_round_begin": (i32, [C.POINTER(TreeState), vp]),
     "ls_grow_workspace_bytes": (i64, [i32, i32]),

@@ -570,6 +570,37 @@ __global__ void __launch_bounds__(256) peer_gather_wait_kernel(uint4* __restrict
     }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) peer_sum_wait_kernel(T* __restrict__ dst, int64_t n4, int64_t slot4, const ls_xchg x) {
+    const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(x.local_sync);
+    if (threadIdx.x < x.world) {
+        const uint32_t* flag = x.peer_flags[x.rank] + threadIdx.x;
+        while (static_cast<int32_t>(ld_acquire_sys(flag) - (epoch + 1)) < 0) { }
+    }
+    __syncthreads();
+    const float4* src = reinterpret_cast<const float4*>(x.peer_o[x.rank]) + static_cast<int64_t>(epoch & 1) * x.world * slot4;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float4 acc = __ldcg(src + i);
+        for (int r = 1; r < x.world; ++r) {                       // rank order: the same sum on every rank
+            const float4 v = __ldcg(src + r * slot4 + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        uint2 pk;
+        pk.x = Num<T>::pack(acc.x, acc.y);
+        pk.y = Num<T>::pack(acc.z, acc.w);
+        reinterpret_cast<uint2*>(dst)[i] = pk;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t ticket = atomicAdd(x.local_sync + 2, 1u);
+        if (ticket == gridDim.x - 1) {
+            x.local_sync[2] = 0;
+            x.local_sync[0] = epoch + 1;
+        }
+    }
+}
+
 static int validate(const ls_attn_desc* d) {
     LS_REQUIRE(d != nullptr, "ls_attn: null descriptor");
     LS_REQUIRE(d->q && d->out && d->k_pool && d->v_pool && d->page_table && d->kv_len_ptr && d->n_q_ptr,
@@ -699,7 +730,7 @@ extern "C" int ls_peer_push(const void* src, int64_t bytes, int64_t slot_bytes, 
     int rc = validate_gather(src, bytes, slot_bytes, x, "ls_peer_push");
     if (rc) return rc;
     const int64_t n16 = bytes / 16;
-    const int blocks = static_cast<int>(n16 / 256 + 1 < 32 ? n16 / 256 + 1 : 32);
+    const int blocks = static_cast<int>(n16 / 256 + 1 < 148 ? n16 / 256 + 1 : 148);
     peer_push_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(src), n16, slot_bytes / 16, *x);
     return check_launch("ls_peer_push");
 }
@@ -712,4 +743,19 @@ extern "C" int ls_peer_gather_wait(void* dst, int64_t bytes, int64_t slot_bytes,
     const int blocks = static_cast<int>(total / 256 + 1 < 32 ? total / 256 + 1 : 32);
     peer_gather_wait_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<uint4*>(dst), n16, slot_bytes / 16, *x);
     return check_launch("ls_peer_gather_wait");
+}
+
+extern "C" int ls_peer_sum_wait(void* dst, int64_t n_elems, int32_t dtype, int64_t slot_bytes, const ls_xchg* x, void* stream) {
+    using namespace ls;
+    int rc = validate_gather(dst, n_elems * 4, slot_bytes, x, "ls_peer_sum_wait");
+    if (rc) return rc;
+    LS_REQUIRE(dtype == LS_F16 || dtype == LS_BF16, "ls_peer_sum_wait: bad dtype %d", dtype);
+    const int64_t n4 = n_elems / 4;
+    const int blocks = static_cast<int>(n4 / 256 + 1 < 148 ? n4 / 256 + 1 : 148);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == LS_F16)
+        peer_sum_wait_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<__half*>(dst), n4, slot_bytes / 16, *x);
+    else
+        peer_sum_wait_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<__nv_bfloat16*>(dst), n4, slot_bytes / 16, *x);
+    return check_launch("ls_peer_sum_wait");
 }

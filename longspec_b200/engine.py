@@ -332,7 +332,49 @@ class Engine:
         # longer.  LONGSPEC_FUSE_COMBINE=1 turns it on.
         self.fuse_sync = torch.zeros(2 * d.kv_heads, dtype=torch.int32, device=dev) \
             if world == 1 and os.environ.get("LONGSPEC_FUSE_COMBINE", "0") == "1" else None
+        # Tensor-parallel MLP (multi-GPU decode rounds): the MLP is 70 % of the per-layer weight bytes that every rank would
+        # otherwise stream in full.  Rank r keeps rows [r, r+1) * ffn / world of gate and up (column-parallel, no exchange)
+        # and the matching columns of down (row-parallel): its fp32 partial [rows, hidden] is pushed to every peer and
+        # the sum is rounded once, like the single-GPU GEMM output.  The prefill keeps the replicated weights (untimed).
+        self.tp = None
+        if (world > 1 and self.peer is not None and os.environ.get("LONGSPEC_TP_MLP", "1") != "0"
+                and d.ffn % world == 0 and (d.ffn // world) % 8 == 0):
+            key = (world, sh.rank)
+            cache = getattr(self.w, "tp_cache", None)
+            if cache is None:
+                cache = self.w.tp_cache = {}
+            if key not in cache:
+                f, fl = d.ffn, d.ffn // world
+                r0, r1 = sh.rank * fl, (sh.rank + 1) * fl
+
+                def shard(L):
+                    return dict(gu=torch.cat([L["gu"][r0:r1], L["gu"][f + r0:f + r1]], 0).contiguous(),
+                                down=L["down"][:, r0:r1].contiguous())
+                cache[key] = dict(layers=[shard(L) for L in self.w.layers], draft=shard(self.w.draft))
+            self.tp = cache[key]
+            self.tp_slot = (self.q_v * d.hidden * 4 + 15) // 16 * 16
+            if self.tp_slot > self.peer.block_o * 4:
+                self.tp = None
+        self.parallelism = "single GPU" if world == 1 else (
+            f"prefix KV sequence-sharded over {world} GPUs (exchange: {self.exchange})"
+            + ("; lm_head vocab-sharded" if self.vshard is not None else "; lm_head replicated")
+            + ("; MLP tensor-parallel, fp32 partial sums all-reduced over peer memory" if self.tp is not None else "; MLP replicated")
+            + "; attention / qkv / o weights replicated")
         self.descs = []                                # keep ctypes structs alive
+
+    def _mlp(self, x, L, shard):
+        """down(silu(gate(x)) * up(x)) -> [rows, hidden] in dtype; tensor-parallel over the ranks in decode rounds."""
+        if shard is None:
+            return F.linear(self._silu_mul(F.linear(x, L["gu"])), L["down"])
+        rows = x.shape[0]
+        act = self._silu_mul(F.linear(x, shard["gu"]))
+        part = torch.mm(act, shard["down"].t(), out_dtype=torch.float32)          # this rank's fp32 partial sums
+        out = torch.empty(rows, self.dims.hidden, dtype=self.dtype, device=self.device)
+        nb = rows * self.dims.hidden * 4
+        _lib.call("ls_peer_push", _ptr(part), nb, self.tp_slot, self.peer.ref, _stream())
+        _lib.call("ls_peer_sum_wait", _ptr(out), rows * self.dims.hidden, self.code, self.tp_slot, self.peer.ref, _stream())
+        self.launches += 2
+        return out
 
     # ------------------------------------------------------------------ kernels
     def _desc(self, q, out, pools, layer, kv_len_ptr, n_q_ptr, q_rows, n_splits, *, kv_len_bias=0, n_tail=0,
@@ -468,8 +510,7 @@ class Engine:
                        n_tail=n_tail, tail_mask=tail_mask, causal=causal)
             o = F.linear(attn, L["o"])
             x = self._norm(h, o, L["ln2"])
-            gu = F.linear(x, L["gu"])
-            delta = F.linear(self._silu_mul(gu), L["down"])
+            delta = self._mlp(x, L, self.tp["layers"][li] if self.tp is not None else None)
         return h, delta
 
     def verify(self):
@@ -550,7 +591,7 @@ class Engine:
         o2 = F.linear(attn2, D["ca_o"])
         # --- FFN
         x = self._norm(h, o2, D["ln3"])
-        m = F.linear(self._silu_mul(F.linear(x, D["gu"])), D["down"])
+        m = self._mlp(x, D, self.tp["draft"] if self.tp is not None else None)
         h = h + m
         # --- lm_head + fused log-softmax / cumulative score / top-k / mask bookkeeping
         if level == 0:
