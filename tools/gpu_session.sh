@@ -19,8 +19,9 @@ cut -c1-300 gpurun_out/bench_reference_arm.json
 ( timeout 300 python tools/prof_attn.py 131072 12 > gpurun_out/prof_attn_128k.txt 2>&1 ); tail -3 gpurun_out/prof_attn_128k.txt
 ( timeout 300 python tools/prof_attn.py 16384 30 > gpurun_out/prof_attn_16k.txt 2>&1 ); tail -3 gpurun_out/prof_attn_16k.txt
 ( timeout 600 python tools/prof_round.py 131072 > gpurun_out/prof_round_128k.txt 2>&1 )
-( timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1 )
+# launch list of the TIMED rounds only (bench.py brackets them with cudaProfilerStart/Stop: the prefill alone is > 10^5 launches)
+( LONGSPEC_PROFILE_RANGE=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1 )
 wc -l gpurun_out/launches_bench.csv
 ( timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_tc -s 3 -c 2 -o gpurun_out/attn_tc_full -f \
     python tools/prof_attn.py 131072 3 > gpurun_out/ncu_full.log 2>&1 )

@@ -40,8 +40,8 @@ def launches():
     # the decode rounds are the launches after the last ls_round_begin-delimited boundary: take the LAST full round
     idx = [i for i, r in enumerate(rows) if "round_begin" in r[1]]
     with open(os.path.join(PROF, f"{tag}_launches_bench.txt"), "w") as f:
-        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 2 --warmup 3 --no-cpu-baseline\n")
-        f.write(f"# {len(rows)} launches in the process (prefill + eager round + graph rounds + roofline loop); "
+        f.write(f"# LONGSPEC_PROFILE_RANGE=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 2 --warmup 3 --no-cpu-baseline\n")
+        f.write(f"# {len(rows)} launches inside the profiled range (the timed graph replays); "
                 f"{len(idx)} decode rounds seen.\n# Per-launch times are cold-cache and serialised: compare SHARES.\n")
         if len(idx) >= 2:
             a, b = idx[-2], idx[-1]
