@@ -1,7 +1,7 @@
 """-m gpu: the UNMODIFIED reference driver (longspec/test/inference_long-bench.py) run against the drop-in.
 
-The driver file is executed as shipped (runpy) from $LONGSPEC_REF_DIR, /root/reference or baseline/_ref (git-ignored,
-travels with the gpurun snapshot) - the test is skipped where none of them holds the file.  `from llama_glide import LlamaGlide` resolves to
+The driver file is executed as shipped (runpy) from $LONGSPEC_REF_DIR or /root/reference - the test is skipped where
+neither holds the file (a reference checkout is never copied into this repo).  `from llama_glide import LlamaGlide` resolves to
 dropin/llama_glide.py; the hub ids the driver passes ("lmsys/vicuna-7b-v1.5-16k", "sail/longspec-vicuna-7b-v1.5-16k")
 resolve through a LOCAL Hugging Face cache that the test fills with a toy-width checkpoint (real AutoConfig, real
 snapshot lookup, safetensors in the reference's key names); only the tokenizer is a stub (no tokenizer files offline)
@@ -21,9 +21,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _ref_dir():
-    # baseline/_ref is git-ignored (never part of this repo's history) but travels to the GPU box with the snapshot: the
-    # build container drops the UNMODIFIED driver file there so that this test also runs where /root/reference is absent
-    for d in (os.environ.get("LONGSPEC_REF_DIR"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+    # The reference tree never travels with this repo: the test runs wherever a checkout of sail-sg/LongSpec is mounted
+    # (LONGSPEC_REF_DIR=/path/to/LongSpec) next to a GPU and is skipped elsewhere.  profiles/r02_driver_test.log is the
+    # record of the B200 run of round 2.
+    for d in (os.environ.get("LONGSPEC_REF_DIR"), "/root/reference"):
         if d and os.path.exists(os.path.join(d, "longspec", "test", "inference_long-bench.py")):
             return d
     return None
