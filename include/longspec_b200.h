@@ -116,6 +116,12 @@ int ls_attn_partial(const ls_attn_desc* d, void* stream);
 /* 1 if ls_attn_partial(d) will merge the slots and write d->out itself (d->fuse_sync set and the conditions above hold),
  * 0 if the caller has to run ls_attn_combine, negative on a bad descriptor.  No GPU work. */
 int ls_attn_fuses_combine(const ls_attn_desc* d);
+/* Tuning knob, no reference counterpart: which tcgen05 kernel serves calls with three row tiles (257..384 packed rows,
+ * the Llama-3 / QwQ verify shapes).  0 = two row tiles per CTA in heavy/heavy/light trios, 1 = one row tile per CTA
+ * (default), 2 = one row tile per CTA in clusters of two with TMA multicast of the K/V tiles.  Sets the mode when
+ * 0 <= mode <= 2 and returns the previous one (pass -1 to query); the environment variable LONGSPEC_TC1 gives the
+ * initial value.  Results of the three agree within the rounding of P to the 16-bit type. */
+int ls_attn_tc1_mode(int mode);
 /* the general mma.sync data path behind ls_attn_partial (kept callable for cross-checks) */
 int ls_attn_partial_mma(const ls_attn_desc* d, void* stream);
 /* the tcgen05/TMA data path alone: unmasked full 128-key tiles of the prefix into n_splits_tc slots (window < 0,

@@ -58,6 +58,7 @@ _SIGS = {
     "ls_sm_count": (i32, []),
     "ls_attn_partial": (i32, [C.POINTER(AttnDesc), vp]),
     "ls_attn_fuses_combine": (i32, [C.POINTER(AttnDesc)]),
+    "ls_attn_tc1_mode": (i32, [i32]),
     "ls_attn_partial_mma": (i32, [C.POINTER(AttnDesc), vp]),
     "ls_attn_partial_tc": (i32, [C.POINTER(AttnDesc), i32, vp]),
     "ls_attn_combine": (i32, [C.POINTER(AttnDesc), vp]),

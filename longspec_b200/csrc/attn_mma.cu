@@ -403,6 +403,15 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Wait until a peer's flag shows `epoch`.  A peer that died or fell out of step must not hang this GPU for ever: after
+// ~20 s of spinning (far beyond any legitimate wait - a whole 128k prefill block exchange takes microseconds) the kernel
+// traps, which surfaces as a CUDA error on the host instead of a silent hang.
+__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch) {
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(ld_acquire_sys(flag) - epoch) < 0) {
+        if (clock64() - t0 > 40000000000ll) __trap();
+    }
+}
 
 // One warp per (packed row, kv head): merge this launch's own slots (like attn_combine_kernel<REDUCE>) and store the
 // normalised fp32 row + LSE into block `rank` of EVERY rank's exchange buffer; the last CTA publishes the epoch.
@@ -480,7 +489,7 @@ __global__ void __launch_bounds__(256) attn_combine_wait_kernel(const ls_attn_de
     const int par = epoch & 1;
     if (threadIdx.x < x.world) {
         const uint32_t* flag = x.peer_flags[x.rank] + threadIdx.x;
-        while (static_cast<int32_t>(ld_acquire_sys(flag) - (epoch + 1)) < 0) { }
+        wait_flag(flag, epoch + 1);
     }
     __syncthreads();
     if (warp_global < Rtot * d.n_kv_heads) {
@@ -550,7 +559,7 @@ __global__ void __launch_bounds__(256) peer_gather_wait_kernel(uint4* __restrict
     const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(x.local_sync);
     if (threadIdx.x < x.world) {
         const uint32_t* flag = x.peer_flags[x.rank] + threadIdx.x;
-        while (static_cast<int32_t>(ld_acquire_sys(flag) - (epoch + 1)) < 0) { }
+        wait_flag(flag, epoch + 1);
     }
     __syncthreads();
     const uint4* src = reinterpret_cast<const uint4*>(x.peer_o[x.rank]) + static_cast<int64_t>(epoch & 1) * x.world * slot16;
@@ -575,7 +584,7 @@ __global__ void __launch_bounds__(256) peer_sum_wait_kernel(T* __restrict__ dst,
     const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(x.local_sync);
     if (threadIdx.x < x.world) {
         const uint32_t* flag = x.peer_flags[x.rank] + threadIdx.x;
-        while (static_cast<int32_t>(ld_acquire_sys(flag) - (epoch + 1)) < 0) { }
+        wait_flag(flag, epoch + 1);
     }
     __syncthreads();
     const float4* src = reinterpret_cast<const float4*>(x.peer_o[x.rank]) + static_cast<int64_t>(epoch & 1) * x.world * slot4;

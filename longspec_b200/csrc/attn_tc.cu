@@ -43,6 +43,7 @@
 // restated in oracle/flash_ref.py and oracle/attention.py.
 #include <cuda.h>
 #include <limits.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <type_traits>
@@ -132,6 +133,20 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Cluster flavours (attn_tc1_kernel<T, true>): the same K / V tile feeds both CTAs of a pair, so each CTA loads one
+// 64-element half and multicasts it into both shared memories; "stage free" commits arrive on both CTAs' barriers.
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+                 ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // Descriptors are (lo, hi) register pairs; hi is identical for every operand of this kernel (SBO = 1024 B,
 // descriptor version 1, SWIZZLE_128B), lo = (smem address >> 4) | (LBO >> 4) << 16, so stepping along K is
@@ -326,6 +341,76 @@ __device__ __forceinline__ float exp_phase(const uint32_t (&sv)[64], uint32_t bu
     return a0 + a1;
 }
 
+// The same phase with P left in registers (attn_tc1_kernel stores it once the P columns are free).
+template <typename T, int POLY>
+__device__ __forceinline__ float exp_regs(const uint32_t (&sv)[64], uint32_t (&pk)[32], uint64_t c2x2, uint64_t negm) {
+    uint64_t sum_a = 0ull, sum_b = 0ull;
+#pragma unroll
+    for (int e = 0; e < 64; e += 2) {
+        const uint64_t x2 = fma2(pack2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), c2x2, negm);
+        float p0, p1;
+        if ((e & 7) < POLY) {
+            exp2_poly2(x2, p0, p1);
+        } else {
+            float x0, x1;
+            unpack2(x2, x0, x1);
+            p0 = fast_exp2(x0);
+            p1 = fast_exp2(x1);
+        }
+        if (e & 2) sum_b = add2(sum_b, pack2(p0, p1)); else sum_a = add2(sum_a, pack2(p0, p1));
+        pk[e >> 1] = Num<T>::pack(p0, p1);
+    }
+    float a0, a1;
+    unpack2(add2(sum_a, sum_b), a0, a1);
+    return a0 + a1;
+}
+
+// The masked remainder of a call as SPECIAL tiles appended to the tile sequence: the prefix keys behind the last full
+// unmasked tile (partial tile, causal rows) and the tree-masked tail of this round's tokens.  Thread 0 writes the table
+// (visible after the next CTA barrier); every thread gets the count.
+__device__ __forceinline__ int plan_special_tiles(const ls_attn_desc& d, int kv_len, int total_tiles, SpecialTile* sp_tiles, int tid) {
+    const int sb = d.kv_shard_begin;
+    const int se = d.kv_shard_end < 0 ? INT_MAX : d.kv_shard_end;
+    const int loc_end = max(min(kv_len, se) - sb, 0);
+    int n = 0;
+    for (int tok = total_tiles * BN; tok < loc_end && n < MAX_SPECIAL; tok += BN, ++n)
+        if (tid == 0) sp_tiles[n] = SpecialTile{tok, min(BN, loc_end - tok), 0, tok + sb};
+    if (d.tail_owner) {
+        const int t0 = kv_len - sb, t1 = t0 + d.n_tail;
+        for (int tok = t0; tok < t1 && n < MAX_SPECIAL; ++n) {
+            const int len = min(LS_PAGE - (tok & (LS_PAGE - 1)), t1 - tok);   // never cross a page
+            if (tid == 0) sp_tiles[n] = SpecialTile{tok, len, 1, tok - t0};
+            tok += len;
+        }
+    }
+    return n;
+}
+
+// Visibility word of packed row rp for the 64 key slots of half h of a special tile
+__device__ __forceinline__ uint64_t special_visibility(const ls_attn_desc& d, const SpecialTile& st, int rp, int R, int G,
+                                                       int kv_len, int n_q, int h) {
+    uint64_t vis = 0ull;
+    if (rp < R) {
+        const int qi = rp / G;
+        if (st.kind == 0) {
+            const int hi = d.causal ? kv_len - (n_q - 1 - qi) : kv_len;      // visible global keys: key < hi
+            const int cnt = min(max(hi - st.base, 0), st.n_valid) - h * 64;
+            vis = cnt >= 64 ? ~0ull : (cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull));
+        } else {
+            const uint64_t* w = d.tail_mask + static_cast<size_t>(qi) * LS_MASK_WORDS;
+            const int k0 = st.base + h * 64;
+            const int wi = k0 >> 6, sh = k0 & 63;
+            if (wi < LS_MASK_WORDS) {
+                vis = w[wi] >> sh;
+                if (sh && wi + 1 < LS_MASK_WORDS) vis |= w[wi + 1] << (64 - sh);
+            }
+            const int cnt = st.n_valid - h * 64;
+            if (cnt < 64) vis &= cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull);
+        }
+    }
+    return vis;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
@@ -341,28 +426,10 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
     const int R = n_q * G;
     const int kv_len = *d.kv_len_ptr + d.kv_len_bias;
     const int total_tiles = tc_full_tiles(d, kv_len, n_q);
-    // With `fuse` the masked remainder rides along as SPECIAL tiles appended to the tile sequence: the prefix keys
-    // behind the last full unmasked tile (partial tile, causal rows) and the tree-masked tail of this round's
-    // tokens.  They come from a small table in shared memory and the softmax applies a per-row bit mask to them.
+    // With `fuse` the masked remainder rides along as SPECIAL tiles appended to the tile sequence; they come from a small
+    // table in shared memory and the softmax applies a per-row bit mask to them.
     SpecialTile* sp_tiles = reinterpret_cast<SpecialTile*>(smem + OFF_SPECIAL);
-    int n_special = 0;
-    if (fuse & 1) {
-        const int sb = d.kv_shard_begin;
-        const int se = d.kv_shard_end < 0 ? INT_MAX : d.kv_shard_end;
-        const int loc_end = max(min(kv_len, se) - sb, 0);
-        int n = 0;
-        for (int tok = total_tiles * BN; tok < loc_end && n < MAX_SPECIAL; tok += BN, ++n)
-            if (tid == 0) sp_tiles[n] = SpecialTile{tok, min(BN, loc_end - tok), 0, tok + sb};
-        if (d.tail_owner) {
-            const int t0 = kv_len - sb, t1 = t0 + d.n_tail;
-            for (int tok = t0; tok < t1 && n < MAX_SPECIAL; ++n) {
-                const int len = min(LS_PAGE - (tok & (LS_PAGE - 1)), t1 - tok);   // never cross a page
-                if (tid == 0) sp_tiles[n] = SpecialTile{tok, len, 1, tok - t0};
-                tok += len;
-            }
-        }
-        n_special = n;
-    }
+    const int n_special = (fuse & 1) ? plan_special_tiles(d, kv_len, total_tiles, sp_tiles, tid) : 0;
     const int all_tiles = total_tiles + n_special;
 
     // ---- role of this CTA (see the header comment) -------------------------------------------------
@@ -587,26 +654,7 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
             if (gi >= total_tiles) {
                 // per-row visibility word of this half's 64 key slots
                 const SpecialTile st = sp_tiles[gi - total_tiles];
-                const int rp = rp0 + row;
-                uint64_t vis = 0ull;
-                if (rp < R) {
-                    const int qi = rp / G;
-                    if (st.kind == 0) {
-                        const int hi = d.causal ? kv_len - (n_q - 1 - qi) : kv_len;      // visible global keys: key < hi
-                        const int cnt = min(max(hi - st.base, 0), st.n_valid) - h * 64;
-                        vis = cnt >= 64 ? ~0ull : (cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull));
-                    } else {
-                        const uint64_t* w = d.tail_mask + static_cast<size_t>(qi) * LS_MASK_WORDS;
-                        const int k0 = st.base + h * 64;
-                        const int wi = k0 >> 6, sh = k0 & 63;
-                        if (wi < LS_MASK_WORDS) {
-                            vis = w[wi] >> sh;
-                            if (sh && wi + 1 < LS_MASK_WORDS) vis |= w[wi + 1] << (64 - sh);
-                        }
-                        const int cnt = st.n_valid - h * 64;
-                        if (cnt < 64) vis &= cnt <= 0 ? 0ull : ((1ull << cnt) - 1ull);
-                    }
-                }
+                const uint64_t vis = special_visibility(d, st, rp0 + row, R, G, kv_len, n_q, h);
 #pragma unroll
                 for (int e = 0; e < 64; ++e)
                     if (!((vis >> e) & 1ull)) sv[e] = 0xff800000u;                       // -inf
@@ -781,7 +829,10 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
             asm volatile("bar.sync 1, 512;" ::: "memory");
             if (tid == 128) {
                 atomicAdd(arrive, 1u);
-                while (*reinterpret_cast<volatile uint32_t*>(arrive) < gridDim.x) { }
+                const long long t0 = clock64();
+                while (*reinterpret_cast<volatile uint32_t*>(arrive) < gridDim.x) {
+                    if (clock64() - t0 > 40000000000ll) __trap();        // ~20 s: a CTA of this head never arrived
+                }
                 __threadfence();
             }
             asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -825,6 +876,432 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
         tc_fence_before();
     }
     __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+    }
+}
+
+// ======================================================================================================================
+// attn_tc1_kernel: ONE row tile per CTA, for calls with three row tiles (the Llama-3 / QwQ verify shapes).
+//
+// The two-row-tile kernel above is bound by three costs that sit within 10 % of each other: the
+// shared-memory operand port under the SS QK^T MMAs, the S -> softmax -> P -> PV round trip through a buffer that P
+// shares with S, and MUFU.  With one row tile per CTA there is TMEM room to remove the first two:
+//
+//   TMEM (512 columns) = O accumulators 2 x 128 | S 128 | P 64 | Q 64
+//
+//   * Q lives in TMEM (written once by the softmax warps with tcgen05.st): QK^T is a TS MMA that reads only the 4 KB K
+//     slice from shared memory per K step (8 KB with Q in shared memory: 80-82 instead of 57 cycles per MMA).
+//   * S is released as soon as its 128 x 128 scores sit in registers (S_FREE) and P has columns of its own, so QK(p+2)
+//     runs while pair p is still in softmax.  Issue order  QK(0) QK(1) | QK(2) PV(0) | QK(3) PV(1) | ...
+//     P(p) is stored only once PV(p-1) has drained the P columns (PV_DONE) - the exponentials are already in registers.
+//   * Pairs alternate between the two accumulators (= softmax warpgroup pairs b = p & 1), each with its own reference
+//     maxima, exactly like the single-row-tile mode above; the epilogue merges the two partial states.
+//
+// A trio = row tiles 0, 1, 2 over the SAME key tiles (the range of two partial slots).  Every CTA now needs every K / V
+// tile of its trio, so with CLUSTER the CTAs of row tiles 0 and 1 form a cluster of two (one TPC): each loads one
+// 64-element half of every tile and TMA-multicasts it into both shared memories; a stage is free again when BOTH
+// CTAs' MMAs have released it (multicast tcgen05.commit onto both EMPTY barriers, count 2).  The row-tile-2 CTAs are
+// clustered in twos as well (the launch attribute is grid-wide) but run independently.  L2 -> SM traffic stays at twice
+// the algorithmic bytes, as before.
+namespace one {
+constexpr int STAGES1 = 3;
+constexpr int OFF_K1 = 0;
+constexpr int OFF_V1 = OFF_K1 + STAGES1 * TILE_BYTES;
+constexpr int OFF_STATE1 = OFF_V1 + STAGES1 * TILE_BYTES;
+constexpr int OFF_BAR1 = OFF_STATE1 + STATE_BYTES;
+constexpr int OFF_SPECIAL1 = OFF_BAR1 + BAR_BYTES;
+constexpr int SMEM1_BYTES = OFF_SPECIAL1 + SPECIAL_BYTES + 1024;
+static_assert(SMEM1_BYTES <= 232448, "attn_tc1_kernel: shared memory exceeds the 227 KB opt-in limit");
+static_assert(128 * OUT_STRIDE * 4 <= OFF_STATE1, "epilogue staging must fit in the K / V rings");
+constexpr uint32_t COL1_O = 0;                     // 2 x 128
+constexpr uint32_t COL1_S = 256;                   // 128 fp32 score columns
+constexpr uint32_t COL1_P = 384;                   // 128 keys x 16 bit = 64 columns
+constexpr uint32_t COL1_Q = 448;                   // 128 head dims x 16 bit = 64 columns
+enum { K_FULL = 0, K_EMPTY = 3, V_FULL = 6, V_EMPTY = 9, S_FULL = 12, S_FREE = 14, P_FULL = 16, PV_DONE = 18, ALL_DONE = 20, N_BARS = 21 };
+static_assert(N_BARS * 8 + 8 <= BAR_BYTES, "barrier block too small");
+// S_FREE / P_FULL arrivals of a softmax warpgroup pair: one per warp (lane 0, behind the warp-collective tcgen05.wait)
+// instead of one per thread - 32 x fewer shared-memory atomics on the two hand-offs that sit on the critical path.
+#ifndef LS_TC1_THREAD_ARRIVE
+constexpr uint32_t ARRIVALS1 = 8;
+__device__ __forceinline__ void group_arrive(uint32_t bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+#else
+constexpr uint32_t ARRIVALS1 = 256;
+__device__ __forceinline__ void group_arrive(uint32_t bar, int) { mbar_arrive(bar); }
+#endif
+}  // namespace one
+
+template <typename T, bool CLUSTER>
+__global__ void __launch_bounds__(THREADS, 1)
+attn_tc1_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                int n_slots, int fuse) {
+    using namespace one;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment (SWIZZLE_128B atoms) of the SHARED-WINDOW offset, not of the generic pointer: in a cluster
+    // launch the generic address of a CTA's shared memory depends on its rank, and the CTA-relative offsets of the two
+    // CTAs of a multicast pair must agree.
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bx = blockIdx.x, kvh = blockIdx.y;
+    LS_TRACE_INIT
+    const int G = d.n_heads / d.n_kv_heads;
+    const int n_q = min(*d.n_q_ptr, d.q_rows);
+    const int R = n_q * G;
+    const int kv_len = *d.kv_len_ptr + d.kv_len_bias;
+    const int total_tiles = tc_full_tiles(d, kv_len, n_q);
+    SpecialTile* sp_tiles = reinterpret_cast<SpecialTile*>(smem + OFF_SPECIAL1);
+    const int n_special = (fuse & 1) ? plan_special_tiles(d, kv_len, total_tiles, sp_tiles, tid) : 0;
+    const int all_tiles = total_tiles + n_special;
+
+    // ---- role: trio g = the key tiles of slots 2g, 2g+1; CTAs [0, 2T) = row tiles 0 / 1 (bx & 1) of trio bx >> 1,
+    // CTAs [2T, 3T) = row tile 2 of trio bx - 2T.  The merged state goes to slot 2g, slot 2g+1 is written empty.
+    const int n_trios = (n_slots + 1) >> 1;
+    const bool light = bx >= 2 * n_trios;
+    const int g = light ? bx - 2 * n_trios : bx >> 1;
+    const int rt = light ? 2 : (bx & 1);
+    const int share0 = 2 * g;
+    const int nshare = min(2, n_slots - share0);
+    const int slot = share0, empty_slot = nshare == 2 ? share0 + 1 : -1;
+    const bool mc = CLUSTER && !light;                               // this CTA shares its K / V tiles with its cluster peer
+    const uint32_t cta_rank = static_cast<uint32_t>(bx & 1);         // rank in the cluster of two (cluster dims (2, 1, 1))
+    const bool rows_live = rt * 128 < R;                             // this CTA's row tile has rows at run time
+    // a multicast pair runs its pipeline whenever the PAIR has live rows (row tile 0): the peer depends on this CTA's loads
+    const bool run = mc ? R > 0 : rows_live;
+    const int per = (all_tiles + n_slots - 1) / n_slots;
+    const int tile_lo = min(share0 * per, all_tiles);
+    const int tile_hi = min((share0 + nshare) * per, all_tiles);
+    const int n_pairs = run ? tile_hi - tile_lo : 0;                 // one pair per key tile; pair p -> accumulator p & 1
+
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR1 + N_BARS * 8);
+    const uint32_t bar0 = sbase + OFF_BAR1;
+    auto bar = [&](int i) { return bar0 + i * 8; };
+
+    if (tid == 0) {
+        for (int i = 0; i < STAGES1; ++i) {
+            mbar_init(bar(K_FULL + i), 1); mbar_init(bar(K_EMPTY + i), mc ? 2 : 1);
+            mbar_init(bar(V_FULL + i), 1); mbar_init(bar(V_EMPTY + i), mc ? 2 : 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar(S_FULL + i), 1); mbar_init(bar(S_FREE + i), ARRIVALS1);
+            mbar_init(bar(P_FULL + i), ARRIVALS1); mbar_init(bar(PV_DONE + i), 1);
+        }
+        mbar_init(bar(ALL_DONE), 2);                 // the QK issuer and the PV issuer
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (CLUSTER) cluster_sync_all();               // the peer's barriers are initialised before anything is multicast at them
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    constexpr int FMT = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+    constexpr uint32_t IDESC_QK = make_idesc(128, 128, FMT, 0, 0);
+    constexpr uint32_t IDESC_PV = make_idesc(128, 128, FMT, 0, 1);
+
+    if (warp < 4) {
+        reg_dec<REGS_CTRL>();
+        if (warp == 0) {
+            // ================= TMA producer =================
+            int s = 0, ph = 0;
+            for (int j = 0; j < n_pairs; ++j) {
+                const int gi = tile_lo + j;
+                const int tok = gi >= total_tiles ? sp_tiles[gi - total_tiles].tok : gi * BN;
+                const int page = __ldg(d.page_table + (tok >> 7));
+                const int row = (page * d.n_kv_heads + kvh) * LS_PAGE + (tok & (LS_PAGE - 1));
+                mbar_wait(bar(K_EMPTY + s), ph ^ 1);
+                if (elect_one()) {
+                    const uint32_t dst = sbase + OFF_K1 + s * TILE_BYTES;
+                    mbar_expect_tx(bar(K_FULL + s), TILE_BYTES);
+                    if (mc) {
+                        tma_load_2d_mc(dst + cta_rank * 16384, &map_k, 64 * cta_rank, row, bar(K_FULL + s), 3);
+                    } else {
+                        tma_load_2d(dst, &map_k, 0, row, bar(K_FULL + s));
+                        tma_load_2d(dst + 16384, &map_k, 64, row, bar(K_FULL + s));
+                    }
+                }
+                __syncwarp();
+                mbar_wait(bar(V_EMPTY + s), ph ^ 1);
+                if (elect_one()) {
+                    const uint32_t dst = sbase + OFF_V1 + s * TILE_BYTES;
+                    mbar_expect_tx(bar(V_FULL + s), TILE_BYTES);
+                    if (mc) {
+                        tma_load_2d_mc(dst + cta_rank * 16384, &map_v, 64 * cta_rank, row, bar(V_FULL + s), 3);
+                    } else {
+                        tma_load_2d(dst, &map_v, 0, row, bar(V_FULL + s));
+                        tma_load_2d(dst + 16384, &map_v, 64, row, bar(V_FULL + s));
+                    }
+                }
+                __syncwarp();
+                if (++s == STAGES1) { s = 0; ph ^= 1; }
+            }
+        } else if (warp == 1) {
+            // ================= QK issuer (converged warp, one elected lane issues) =================
+            // S is a single buffer: QK(q) may only overwrite it once the softmax warps of pair q-1 hold its scores in
+            // registers (S_FREE).  Nothing else orders QK against PV: the two MMA streams are issued by two warps, so
+            // one warp's barrier polls and commits (~ 500 cycles per pair, during which a single issuer feeds nothing
+            // into a tensor pipe that queues barely one instruction) overlap the other warp's MMAs.
+            const uint32_t k_lo = (((sbase + OFF_K1) >> 4) & 0x3FFFu) | LBO_K;          // 14-bit address field: in a cluster the
+                                                                                        // shared address carries the CTA rank above it
+            asm volatile("bar.sync %0, %1;" ::"n"(BAR_Q_READY), "n"(512 + 32) : "memory");     // Q sits in TMEM
+            int sq = 0, phq = 0;                          // K stage / parity
+            for (int q = 0; q < n_pairs; ++q) {
+                mbar_wait(bar(K_FULL + sq), phq);
+                if (q >= 1) mbar_wait(bar(S_FREE + ((q - 1) & 1)), ((q - 1) >> 1) & 1);
+                tc_fence_after();
+                if (lane == 0) LS_TRACE(7, q);
+                if (elect_one()) {
+                    const uint32_t b0 = k_lo + sq * (TILE_BYTES >> 4);
+                    if (!LS_DBG(2))
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        tc_mma_ts(tmem + COL1_S, tmem + COL1_Q + kk * 8, b0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2, IDESC_QK, kk > 0 ? 1u : 0u);
+                    tc_commit(bar(S_FULL + (q & 1)));
+                    if (mc) tc_commit_mc(bar(K_EMPTY + sq), 3); else tc_commit(bar(K_EMPTY + sq));
+                }
+                __syncwarp();
+                if (lane == 0) LS_TRACE(6, q);
+                if (++sq == STAGES1) { sq = 0; phq ^= 1; }
+            }
+            if (n_pairs > 0 && elect_one()) tc_commit(bar(ALL_DONE));
+            __syncwarp();
+        } else if (warp == 3) {
+            // ================= PV issuer =================
+            const uint32_t v_lo = (((sbase + OFF_V1) >> 4) & 0x3FFFu) | LBO_V;
+            int sv_ = 0, phv = 0;                         // V stage / parity
+            for (int p = 0; p < n_pairs; ++p) {
+                mbar_wait(bar(V_FULL + sv_), phv);
+                if (!LS_DBG(8)) mbar_wait(bar(P_FULL + (p & 1)), (p >> 1) & 1);
+                tc_fence_after();
+                if (lane == 0) LS_TRACE(0, p);
+                if (elect_one()) {
+                    const uint32_t b0 = v_lo + sv_ * (TILE_BYTES >> 4);
+                    const uint32_t dst = tmem + COL1_O + (p & 1) * 128;
+                    if (!LS_DBG(1))
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        tc_mma_ts(dst, tmem + COL1_P + kk * 8, b0 + kk * (2048 >> 4), IDESC_PV, (p >= 2 || kk > 0) ? 1u : 0u);
+                    tc_commit(bar(PV_DONE + (p & 1)));
+                    if (mc) tc_commit_mc(bar(V_EMPTY + sv_), 3); else tc_commit(bar(V_EMPTY + sv_));
+                }
+                __syncwarp();
+                if (lane == 0) LS_TRACE(1, p);
+                if (++sv_ == STAGES1) { sv_ = 0; phv ^= 1; }
+            }
+            if (n_pairs > 0 && elect_one()) tc_commit(bar(ALL_DONE));
+            __syncwarp();
+        }
+    } else {
+        reg_inc<REGS_SOFTMAX>();
+        const int wgi = (warp - 4) >> 2;
+        const int b = wgi >> 1, h = wgi & 1;
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const uint32_t lane_addr = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+        const int rp0 = rt * 128;
+        // Q -> TMEM: thread (warpgroup, lane quarter, lane) owns 32 head dims (16 packed columns) of its row
+        if (n_pairs > 0) {
+            uint32_t qr[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) qr[e] = 0u;
+            const int rp = rp0 + row;
+            if (rp < R) {
+                const T* __restrict__ q = reinterpret_cast<const T*>(d.q);
+                const size_t q_stride = d.q_stride > 0 ? static_cast<size_t>(d.q_stride) : static_cast<size_t>(d.n_heads) * 128;
+                const int i = rp / G, gg = rp - i * G;
+                const uint4* src = reinterpret_cast<const uint4*>(q + static_cast<size_t>(i) * q_stride + static_cast<size_t>(kvh * G + gg) * 128 + wgi * 32);
+                const uint4 a0 = src[0], a1 = src[1], a2 = src[2], a3 = src[3];
+                qr[0] = a0.x; qr[1] = a0.y; qr[2] = a0.z; qr[3] = a0.w;
+                qr[4] = a1.x; qr[5] = a1.y; qr[6] = a1.z; qr[7] = a1.w;
+                qr[8] = a2.x; qr[9] = a2.y; qr[10] = a2.z; qr[11] = a2.w;
+                qr[12] = a3.x; qr[13] = a3.y; qr[14] = a3.z; qr[15] = a3.w;
+            }
+            LS_TMEM_ST16(lane_addr + COL1_Q + wgi * 16, qr);
+            tmem_wait_st();
+        }
+        tc_fence_before();
+        asm volatile("bar.arrive %0, %1;" ::"n"(BAR_Q_READY), "n"(512 + 32) : "memory");
+
+        // ================= softmax warpgroups (wgi = 2b + h: pairs of parity b, 64-key half h) =================
+        const float c2 = d.scale * 1.4426950408889634f;
+        const uint64_t c2x2 = pack2(c2, c2);
+        const bool warp_valid = rp0 + quad * 32 < R;                 // warp-uniform, the same in both warps of a row
+        const uint32_t o_half = lane_addr + COL1_O + b * 128 + h * 64;
+        const uint32_t s_half = lane_addr + COL1_S + h * 64;         // this thread's 64 score columns
+        const uint32_t p_half = lane_addr + COL1_P + h * 32;         // ... and its 32 packed probability columns
+        const int pair_bar = 2 + b * 4 + quad;
+        float* xch = reinterpret_cast<float*>(smem + OFF_STATE1);    // [2 accumulators][2 halves][128 rows]
+        float m_ref = -INFINITY, l = 0.f;
+        int it = 0;
+        for (int p = b; p < n_pairs && !LS_DBG(8); p += 2, ++it) {
+            mbar_wait(bar(S_FULL + b), it & 1);
+            if (!warp_valid || LS_DBG(4)) {
+                // Padding rows only: keep the barrier protocol, skip the math (their O rows are never read) - at the
+                // live warps' pace: S(p+2) can be ready before pair p has finished, and an early P_FULL arrival for
+                // pair p+2 would be counted into the phase of pair p.  PV(p-1) complete implies P_FULL(p-2) complete.
+                group_arrive(bar(S_FREE + b), lane);
+                if (p >= 1) mbar_wait(bar(PV_DONE + (b ^ 1)), ((p - 1) >> 1) & 1);
+                group_arrive(bar(P_FULL + b), lane);
+                continue;
+            }
+            tc_fence_after();
+            if (quad == 0 && lane == 0 && h == 0) LS_TRACE(2, p);
+            uint32_t sv[64];
+            LS_TMEM_LD32(s_half, sv);
+            LS_TMEM_LD32(s_half + 32, (sv + 32));
+            tmem_wait_ld();
+            tc_fence_before();
+            group_arrive(bar(S_FREE + b), lane);                            // the scores are in registers: QK(p+1) may overwrite S
+            if (quad == 0 && lane == 0 && h == 0) LS_TRACE(3, p);
+            const int gi = tile_lo + p;
+            if (gi >= total_tiles) {
+                const SpecialTile st = sp_tiles[gi - total_tiles];
+                const uint64_t vis = special_visibility(d, st, rp0 + row, R, G, kv_len, n_q, h);
+#pragma unroll
+                for (int e = 0; e < 64; ++e)
+                    if (!((vis >> e) & 1ull)) sv[e] = 0xff800000u;                       // -inf
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 64; e += 8) {
+                mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])));
+                mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])));
+                mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sv[e + 4]), __uint_as_float(sv[e + 5])));
+                mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sv[e + 6]), __uint_as_float(sv[e + 7])));
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c2;
+            uint32_t any;
+            {
+                const uint32_t need = mx > m_ref + 8.0f ? 1u : 0u;   // lazy rescale threshold (2^8)
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred pin, pout;\n\t"
+                    "setp.ne.u32 pin, %1, 0;\n\t"
+                    "bar.red.or.pred pout, %2, 64, pin;\n\t"
+                    "selp.u32 %0, 1, 0, pout;\n\t"
+                    "}" : "=r"(any) : "r"(need), "r"(pair_bar) : "memory");
+            }
+            if (any) {
+                xch[(b * 2 + h) * 128 + row] = mx;
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                const float joint = fmaxf(mx, xch[(b * 2 + (h ^ 1)) * 128 + row]);
+                const float m_new = joint > m_ref + 8.0f ? joint : m_ref;
+                const float alpha = m_ref == -INFINITY ? 0.f : fast_exp2(m_ref - m_new);
+                l *= alpha;
+                m_ref = m_new;
+                if (it >= 1) {
+                    // The accumulator's previous PV is pair p-2.  It was issued after QK(p), so S_FULL(p) does not
+                    // certify it: wait for its own completion.  PV(p-4) is known complete (P(p-2) was only stored
+                    // after PV(p-3), and MMAs complete in order) and PV(p) cannot have run, so the parity is unambiguous.
+                    mbar_wait(bar(PV_DONE + b), (it - 1) & 1);
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t ov[16];
+                        LS_TMEM_LD16(o_half + c * 16, ov);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+                        LS_TMEM_ST16(o_half + c * 16, ov);
+                    }
+                    tmem_wait_st();
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            }
+            const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
+            uint32_t pk[32];
+            if (gi >= total_tiles) l += exp_regs<T, 0>(sv, pk, c2x2, pack2(-m_use, -m_use));
+            else l += exp_regs<T, LS_TC_POLY>(sv, pk, c2x2, pack2(-m_use, -m_use));
+            if (quad == 0 && lane == 0 && h == 0) LS_TRACE(4, p);
+            // The P columns are free once PV(p-1) has read them.  Both PV_DONE barriers are waited on phase by phase
+            // (this one by the other accumulator's warpgroups), so the parity cannot alias.
+            if (p >= 1) {
+                mbar_wait(bar(PV_DONE + (b ^ 1)), ((p - 1) >> 1) & 1);
+                tc_fence_after();
+            }
+            LS_TMEM_ST16(p_half, pk);
+            LS_TMEM_ST16(p_half + 16, (pk + 16));
+            tmem_wait_st();
+            tc_fence_before();
+            group_arrive(bar(P_FULL + b), lane);
+            if (quad == 0 && lane == 0 && h == 0) LS_TRACE(5, p);
+        }
+        // ================= epilogue: merge the two accumulators, normalised partial O + LSE =================
+        const int Rtot = d.q_rows * G;
+        if (n_pairs > 0) {
+            mbar_wait(bar(ALL_DONE), 0);
+            tc_fence_after();
+        }
+        auto part_base = [&](int sl, int rp) { return (static_cast<size_t>(d.part_offset + sl) * d.n_kv_heads + kvh) * Rtot + rp; };
+        float* st_m = xch;                                           // [2][128]
+        float* st_l = xch + 2 * 128;                                 // [2][2][128]
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (h == 0) st_m[b * 128 + row] = m_ref;
+        st_l[(b * 2 + h) * 128 + row] = l;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        float* stage = reinterpret_cast<float*>(smem);               // [128 rows][OUT_STRIDE]: the K ring is dead (every MMA has completed)
+        {
+            const float m0 = st_m[row], m1 = st_m[128 + row];
+            const float l0 = st_l[row] + st_l[128 + row], l1 = st_l[256 + row] + st_l[384 + row];
+            const float m = fmaxf(m0, m1);
+            const float a0 = l0 > 0.f ? fast_exp2(m0 - m) : 0.f, a1 = l1 > 0.f ? fast_exp2(m1 - m) : 0.f;
+            const float lt = l0 * a0 + l1 * a1;
+            const float inv = lt > 0.f ? 1.f / lt : 0.f;
+            const float w0 = a0 * inv, w1 = a1 * inv;
+            const bool live = n_pairs > 0;
+            const int rp = rp0 + row;
+            if (wgi == 0 && rp < R) {
+                d.part_lse[part_base(slot, rp)] = (live && inv > 0.f) ? (m + log2f(lt)) * 0.6931471805599453f : -INFINITY;
+                if (empty_slot >= 0) d.part_lse[part_base(empty_slot, rp)] = -INFINITY;
+            }
+            if (warp_valid) {                                        // warp-uniform (tcgen05.ld is warp-collective)
+                const int col = wgi * 32;
+                uint32_t o0[32], o1[32];
+                if (live) {
+                    LS_TMEM_LD32(lane_addr + COL1_O + col, o0);
+                    LS_TMEM_LD32(lane_addr + COL1_O + 128 + col, o1);
+                    tmem_wait_ld();
+                }
+                float* ps = stage + row * OUT_STRIDE + col;
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                    float x[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        // an accumulator that never received a PV holds stale TMEM bits: select, do not multiply
+                        const float x0 = (live && w0 > 0.f) ? __uint_as_float(o0[e + u]) * w0 : 0.f;
+                        const float x1 = (live && w1 > 0.f) ? __uint_as_float(o1[e + u]) * w1 : 0.f;
+                        x[u] = x0 + x1;
+                    }
+                    *reinterpret_cast<float4*>(ps + e) = make_float4(x[0], x[1], x[2], x[3]);
+                }
+            }
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        {
+            const int sw = warp - 4;                                 // 0..15
+            for (int r = sw; r < 128; r += 16) {
+                const int rp = rp0 + r;
+                if (rp >= R) break;
+                const float4 v = *reinterpret_cast<const float4*>(stage + r * OUT_STRIDE + lane * 4);
+                *reinterpret_cast<float4*>(d.part_o + part_base(slot, rp) * 128 + lane * 4) = v;
+                if (empty_slot >= 0)
+                    *reinterpret_cast<float4*>(d.part_o + part_base(empty_slot, rp) * 128 + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (CLUSTER) cluster_sync_all();               // the peer may still multicast commits at this CTA's barriers until it is done too
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
@@ -903,6 +1380,24 @@ static bool tc_can_fuse_combine(const ls_attn_desc* d, int n_splits_tc) {
     return gx * d->n_kv_heads <= sms;
 }
 
+// Which kernel serves calls with three row tiles: 0 = attn_tc_kernel (heavy / heavy / light trios), 1 = attn_tc1_kernel
+// (one row tile per CTA; measured fastest: default), 2 = attn_tc1_kernel as clusters of two with TMA multicast (less L2
+// traffic, but the lock-step of the pair costs more than it saves).  LONGSPEC_TC1 sets the initial value.
+static int g_tc1_mode = -1;
+static int tc1_mode() {
+    if (g_tc1_mode < 0) {
+        const char* e = getenv("LONGSPEC_TC1");
+        const int m = e ? atoi(e) : 1;
+        g_tc1_mode = m < 0 ? 0 : (m > 2 ? 2 : m);
+    }
+    return g_tc1_mode;
+}
+extern "C" int ls_attn_tc1_mode(int mode) {
+    const int prev = tc1_mode();
+    if (mode >= 0 && mode <= 2) g_tc1_mode = mode;
+    return prev;
+}
+
 static int launch_tc(const ls_attn_desc* d, int n_splits_tc, int fuse_remainder, void* stream) {
     using namespace ls;
     using namespace ls::tc;
@@ -925,9 +1420,40 @@ static int launch_tc(const ls_attn_desc* d, int n_splits_tc, int fuse_remainder,
                             : ensure_dyn_smem(attn_tc_kernel<__nv_bfloat16>, SMEM_BYTES, &smem_ok_bf16, "ls_attn_partial_tc");
     if (rc) return rc;
     const int nrs = (d->q_rows * G + 127) / 128;
-    dim3 grid(nrs > NRL_MAX ? n_splits_tc + (n_splits_tc + 1) / 2 : n_splits_tc, d->n_kv_heads);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int fuse = (fuse_remainder ? 1 : 0) | ((fuse_remainder && tc_can_fuse_combine(d, n_splits_tc)) ? 2 : 0);
+    // Three row tiles: one row tile per CTA (attn_tc1_kernel), as clusters of two when the grid allows it.
+    // (see ls_attn_tc1_mode)
+    const int mode1 = tc1_mode();
+    if (nrs > NRL_MAX && mode1 > 0 && !(fuse & 2)) {
+        const int gx = 3 * ((n_splits_tc + 1) / 2);
+        const bool cluster = mode1 >= 2 && gx % 2 == 0;
+        static unsigned long long ok1[4] = {0, 0, 0, 0};
+        const int which = (d->dtype == LS_F16 ? 0 : 1) + (cluster ? 2 : 0);
+        const void* fn = which == 0   ? reinterpret_cast<const void*>(attn_tc1_kernel<__half, false>)
+                         : which == 1 ? reinterpret_cast<const void*>(attn_tc1_kernel<__nv_bfloat16, false>)
+                         : which == 2 ? reinterpret_cast<const void*>(attn_tc1_kernel<__half, true>)
+                                      : reinterpret_cast<const void*>(attn_tc1_kernel<__nv_bfloat16, true>);
+        rc = ensure_dyn_smem(fn, one::SMEM1_BYTES, &ok1[which], "ls_attn_partial_tc (one row tile per CTA)");
+        if (rc) return rc;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(gx, d->n_kv_heads);
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = one::SMEM1_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = cluster ? 1 : 0;
+        ls_attn_desc dd = *d;
+        int n_slots = n_splits_tc, fz = fuse;
+        void* args[] = {&dd, &mk, &mv, &n_slots, &fz};
+        const cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
+        if (e != cudaSuccess) { set_error("ls_attn_partial_tc: cluster launch failed: %s", cudaGetErrorString(e)); return LS_ERR_CUDA; }
+        return check_launch("ls_attn_partial_tc");
+    }
+    dim3 grid(nrs > NRL_MAX ? n_splits_tc + (n_splits_tc + 1) / 2 : n_splits_tc, d->n_kv_heads);
     if (d->dtype == LS_F16)
         attn_tc_kernel<__half><<<grid, THREADS, SMEM_BYTES, st>>>(*d, mk, mv, n_splits_tc, fuse);
     else

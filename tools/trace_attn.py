@@ -68,3 +68,12 @@ if vs > 60:
     print("  S loaded -> exp done        :", float((e[4, ss] - e[3, ss]).mean()))
     print("  exp done -> P arrived       :", float((e[5, ss] - e[4, ss]).mean()))
     print("  P arrived -> next S_FULL seen (same WG):", float((e[2, 42:vs - 18] - e[5, 40:vs - 20]).mean()))
+
+# one-row-tile kernel (LONGSPEC_TC1 != 0): events 7 / 6 = QK issuer saw its barriers / issued QK(q); 0 / 1 = PV issuer saw P_FULL(p) / issued PV(p)
+if os.environ.get("LONGSPEC_TC1", "2") != "0" and int((e[6] != 0).sum()) > 60:
+    n = int((e[6] != 0).sum())
+    s2 = slice(20, n - 10)
+    print(f"two-issuer view ({n} pairs): QK period {float(np.diff(e[7, s2]).mean()):.0f}, QK barriers seen -> issued {float((e[6, s2] - e[7, s2]).mean()):.0f}, "
+          f"QK issued -> next barriers seen {float((e[7, 21:n - 9] - e[6, s2]).mean()):.0f} | PV period {float(np.diff(e[0, s2]).mean()):.0f}, "
+          f"P_FULL seen -> PV issued {float((e[1, s2] - e[0, s2]).mean()):.0f}, PV issued -> next P_FULL seen {float((e[0, 21:n - 9] - e[1, s2]).mean()):.0f}")
+    print(f"   QK(q) issued -> S_FULL(q) seen by softmax {float((e[2, s2] - e[6, s2]).mean()):.0f}; P(p) arrived -> PV(p) barriers seen {float((e[0, s2] - e[5, s2]).mean()):.0f}")
