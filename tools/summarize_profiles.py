@@ -93,7 +93,8 @@ def full(rep_name="attn_tc_full"):
             tot = 0.0
             for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 tot += float(data[-1][col[name]].replace(",", "")) * scale[units[col[name]]]
-            json.dump({"kernel": "attn_tc_kernel", "workload": "llama3-8b verify shape, 131072 keys, one layer call",
+            kname = re.sub(r"^void ", "", data[-1][col["Kernel Name"]].split("(")[0])
+            json.dump({"kernel": kname, "workload": "llama3-8b verify shape, 131072 keys, one layer call",
                        "dram_bytes_per_launch": tot, "source": f"profiles/{tag}_{rep_name}_summary.txt"},
                       open(os.path.join(PROF, "attn_tc_traffic.json"), "w"))
         except Exception as e:  # noqa: BLE001

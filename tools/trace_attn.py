@@ -44,19 +44,18 @@ for t in range(lo, hi):
     print(f"{t:4d}  " + "  ".join(f"{int(ev[e, t]) - t0:9d}" for e in range(6)))
 import numpy as np  # noqa: E402
 e = ev.numpy().astype(np.int64)
-entry, done = int(e[7, 511]), int(e[7, 510])
+entry = int(e[7, 511])
 nz = e[2][e[2] != 0]
-lastp = e[5][:510][e[5][:510] != 0]
 if entry and nz.size:
-    print(f"CTA bx={os.environ.get('BX', 0)}: kernel entry -> first S_FULL seen {int(nz[0]) - entry} cycles; last P arrived -> epilogue written "
-          f"{done - int(lastp.max()) if lastp.size else 0}; entry -> epilogue written {done - entry}")
+    print(f"CTA bx={os.environ.get('BX', 0)}: kernel entry -> first S_FULL seen {int(nz[0]) - entry} cycles")
+one_row_tile = os.environ.get("LONGSPEC_TC1", "1") != "0"        # attn_tc1_kernel: events 6 / 7 belong to the QK issuer warp
 valid = int((e[0] != 0).sum())
 sl = slice(20, max(valid - 10, 22))
 print(f"MMA warp (per PAIR of steps, {valid} pairs traced):")
 print("  mean pair period            :", float(np.diff(e[0, sl]).mean()))
 print("  P_FULL seen -> pair issued  :", float((e[1, sl] - e[0, sl]).mean()))
 print("  issued -> next P_FULL seen  :", float((e[0, sl.start + 1:sl.stop + 1] - e[1, sl]).mean()))
-if int((e[6] != 0).sum()) > 30:
+if int((e[6] != 0).sum()) > 30 and not one_row_tile:
     print("  P_FULL seen -> PV issued    :", float((e[6, sl] - e[0, sl]).mean()))
     print("  PV issued -> K tile ready   :", float((e[7, sl] - e[6, sl]).mean()))
     print("  K tile ready -> QK issued   :", float((e[1, sl] - e[7, sl]).mean()))
@@ -70,7 +69,7 @@ if vs > 60:
     print("  P arrived -> next S_FULL seen (same WG):", float((e[2, 42:vs - 18] - e[5, 40:vs - 20]).mean()))
 
 # one-row-tile kernel (LONGSPEC_TC1 != 0): events 7 / 6 = QK issuer saw its barriers / issued QK(q); 0 / 1 = PV issuer saw P_FULL(p) / issued PV(p)
-if os.environ.get("LONGSPEC_TC1", "2") != "0" and int((e[6] != 0).sum()) > 60:
+if one_row_tile and int((e[6] != 0).sum()) > 60:
     n = int((e[6] != 0).sum())
     s2 = slice(20, n - 10)
     print(f"two-issuer view ({n} pairs): QK period {float(np.diff(e[7, s2]).mean()):.0f}, QK barriers seen -> issued {float((e[6, s2] - e[7, s2]).mean()):.0f}, "
