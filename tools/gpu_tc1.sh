@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B session for the one-row-tile-per-CTA attention kernel (LONGSPEC_TC1 = 0 old trios, 1 no clusters, 2 clusters of two).
+# A/B session for the one-row-tile-per-CTA attention kernel (LONGSPEC_TC1 = 0 trios, 1 one row tile per CTA, 2 clusters of two): parity per mode, per-launch timings, cycle traces, bench (profiles/r02b_attn_tc1_*).
 # Every step runs under its own timeout; a hang in a parity run aborts the session (exit 124) before anything longer starts.
 set -u
 mkdir -p gpurun_out
