@@ -899,6 +899,11 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
 //   * Pairs alternate between the two accumulators (= softmax warpgroup pairs b = p & 1), each with its own reference
 //     maxima, exactly like the single-row-tile mode above; the epilogue merges the two partial states.
 //
+//   * Warp roles: warp 0 streams the K tiles and warp 2 the V tiles (two independent 3-stage rings - one loop for both
+//     would tie the K ring to the V ring, and QK^T runs up to two pairs ahead of PV), warp 1 issues QK^T and warp 3 PV
+//     (nothing but mbarriers orders the two MMA streams, so one warp's barrier polls and commits overlap the other's
+//     MMAs: the tensor pipe queues barely one instruction - tools/ubench/mma_rate), warps 4-19 are the softmax warps.
+//
 // A trio = row tiles 0, 1, 2 over the SAME key tiles (the range of two partial slots).  Every CTA now needs every K / V
 // tile of its trio, so with CLUSTER the CTAs of row tiles 0 and 1 form a cluster of two (one TPC): each loads one
 // 64-element half of every tile and TMA-multicasts it into both shared memories; a stage is free again when BOTH
@@ -919,8 +924,7 @@ constexpr uint32_t COL1_O = 0;                     // 2 x 128
 constexpr uint32_t COL1_S = 256;                   // 128 fp32 score columns
 constexpr uint32_t COL1_P = 384;                   // 128 keys x 16 bit = 64 columns
 constexpr uint32_t COL1_Q = 448;                   // 128 head dims x 16 bit = 64 columns
-enum { K_FULL = 0, K_EMPTY = 3, V_FULL = 6, V_EMPTY = 9, S_FULL = 12, S_FREE = 14, P_FULL = 16, PV_DONE = 18, ALL_DONE = 20,
-       DEC = 21 /* 8: reference maxima of pair parity b, lane quarter q handed over (variant 2) */, N_BARS = 29 };
+enum { K_FULL = 0, K_EMPTY = 3, V_FULL = 6, V_EMPTY = 9, S_FULL = 12, S_FREE = 14, P_FULL = 16, PV_DONE = 18, ALL_DONE = 20, N_BARS = 21 };
 static_assert(N_BARS * 8 + 8 <= BAR_BYTES, "barrier block too small");
 // S_FREE / P_FULL arrivals of a softmax warpgroup pair: one per warp (lane 0, behind the warp-collective tcgen05.wait)
 // instead of one per thread - 32 x fewer shared-memory atomics on the two hand-offs that sit on the critical path.
@@ -936,22 +940,11 @@ __device__ __forceinline__ void group_arrive(uint32_t bar, int) { mbar_arrive(ba
 #endif
 }  // namespace one
 
-// VARIANT 0: as described above.  1: clusters of two with TMA multicast.  2: ONE accumulator shared by both warpgroup pairs,
-// which frees 128 TMEM columns for a SECOND S tile (O 128 | S 2 x 128 | P 64 | Q 64): the S tile's round trip - the
-// critical loop of variant 0 - leaves the loop.  The price is a reference maximum per row that four threads of four
-// warps have to agree on pair by pair: the pair's warps decide M(p) from M(p-1) and hand it to the other pair's warps
-// through shared memory + one mbarrier per (pair parity, lane quarter); every thread keeps its partial row sum relative
-// to the reference it last used.
-template <typename T, int VARIANT>
+template <typename T, bool CLUSTER>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_tc1_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                 int n_slots, int fuse) {
     using namespace one;
-    constexpr bool CLUSTER = VARIANT == 1;
-    constexpr bool ONE_ACC = VARIANT == 2;
-    constexpr uint32_t COL_S0 = ONE_ACC ? 128u : COL1_S;             // first S tile (ONE_ACC: two tiles, 128 columns apart)
-    constexpr uint32_t S_STEP = ONE_ACC ? 128u : 0u;
-    constexpr uint32_t O_STEP = ONE_ACC ? 0u : 128u;                 // accumulator of pair parity 1
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment (SWIZZLE_128B atoms) of the SHARED-WINDOW offset, not of the generic pointer: in a cluster
     // launch the generic address of a CTA's shared memory depends on its rank, and the CTA-relative offsets of the two
@@ -1003,7 +996,6 @@ attn_tc1_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k,
             mbar_init(bar(P_FULL + i), ARRIVALS1); mbar_init(bar(PV_DONE + i), 1);
         }
         mbar_init(bar(ALL_DONE), 2);                 // the QK issuer and the PV issuer
-        for (int i = 0; i < 8; ++i) mbar_init(bar(DEC + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -1066,20 +1058,15 @@ attn_tc1_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k,
             int sq = 0, phq = 0;                          // K stage / parity
             for (int q = 0; q < n_pairs; ++q) {
                 mbar_wait(bar(K_FULL + sq), phq);
-                if (ONE_ACC) {                            // S tile q & 1 was last used by pair q - 2
-                    if (q >= 2) mbar_wait(bar(S_FREE + (q & 1)), ((q >> 1) - 1) & 1);
-                } else {
-                    if (q >= 1) mbar_wait(bar(S_FREE + ((q - 1) & 1)), ((q - 1) >> 1) & 1);
-                }
+                if (q >= 1) mbar_wait(bar(S_FREE + ((q - 1) & 1)), ((q - 1) >> 1) & 1);
                 tc_fence_after();
                 if (lane == 0) LS_TRACE(7, q);
                 if (elect_one()) {
                     const uint32_t b0 = k_lo + sq * (TILE_BYTES >> 4);
-                    const uint32_t s_tile = tmem + COL_S0 + (q & 1) * S_STEP;
                     if (!LS_DBG(2))
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk)
-                        tc_mma_ts(s_tile, tmem + COL1_Q + kk * 8, b0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2, IDESC_QK, kk > 0 ? 1u : 0u);
+                        tc_mma_ts(tmem + COL1_S, tmem + COL1_Q + kk * 8, b0 + (kk >> 2) * (16384 >> 4) + (kk & 3) * 2, IDESC_QK, kk > 0 ? 1u : 0u);
                     tc_commit(bar(S_FULL + (q & 1)));
                     if (mc) tc_commit_mc(bar(K_EMPTY + sq), 3); else tc_commit(bar(K_EMPTY + sq));
                 }
@@ -1100,12 +1087,11 @@ attn_tc1_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k,
                 if (lane == 0) LS_TRACE(0, p);
                 if (elect_one()) {
                     const uint32_t b0 = v_lo + sv_ * (TILE_BYTES >> 4);
-                    const uint32_t dst = tmem + COL1_O + (p & 1) * O_STEP;
-                    const int first = ONE_ACC ? 1 : 2;    // pairs that start an accumulator
+                    const uint32_t dst = tmem + COL1_O + (p & 1) * 128;
                     if (!LS_DBG(1))
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk)
-                        tc_mma_ts(dst, tmem + COL1_P + kk * 8, b0 + kk * (2048 >> 4), IDESC_PV, (p >= first || kk > 0) ? 1u : 0u);
+                        tc_mma_ts(dst, tmem + COL1_P + kk * 8, b0 + kk * (2048 >> 4), IDESC_PV, (p >= 2 || kk > 0) ? 1u : 0u);
                     tc_commit(bar(PV_DONE + (p & 1)));
                     if (mc) tc_commit_mc(bar(V_EMPTY + sv_), 3); else tc_commit(bar(V_EMPTY + sv_));
                 }
@@ -1151,8 +1137,8 @@ attn_tc1_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k,
         const float c2 = d.scale * 1.4426950408889634f;
         const uint64_t c2x2 = pack2(c2, c2);
         const bool warp_valid = rp0 + quad * 32 < R;                 // warp-uniform, the same in both warps of a row
-        const uint32_t o_half = lane_addr + COL1_O + b * O_STEP + h * 64;
-        const uint32_t s_half = lane_addr + COL_S0 + b * S_STEP + h * 64;   // this thread's 64 score columns
+        const uint32_t o_half = lane_addr + COL1_O + b * 128 + h * 64;
+        const uint32_t s_half = lane_addr + COL1_S + h * 64;         // this thread's 64 score columns
         const uint32_t p_half = lane_addr + COL1_P + h * 32;         // ... and its 32 packed probability columns
         const int pair_bar = 2 + b * 4 + quad;
         float* xch = reinterpret_cast<float*>(smem + OFF_STATE1);    // [2 accumulators][2 halves][128 rows]
@@ -1195,104 +1181,45 @@ attn_tc1_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k,
                 mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sv[e + 6]), __uint_as_float(sv[e + 7])));
             }
             const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c2;
-            if (ONE_ACC) {
-                // One accumulator: the reference M(p) of a row is decided pair by pair, M(p) = joint max of pair p if it
-                // exceeds M(p-1) by more than 2^8, else M(p-1).  M(p-1) comes from the other pair's warps of this lane quarter.
-                float* m_pub = xch + 4 * 128;                        // [pair parity][128 rows]
-                float m_prev = -INFINITY;
-                if (p >= 1) {
-                    mbar_wait(bar(DEC + (b ^ 1) * 4 + quad), (b == 0 ? it - 1 : it) & 1);
-                    m_prev = m_pub[(b ^ 1) * 128 + row];
-                }
-                if (m_prev != m_ref) {                               // bring this thread's partial row sum to M(p-1)
-                    l *= m_ref == -INFINITY ? 0.f : fast_exp2(m_ref - m_prev);
-                    m_ref = m_prev;
-                }
-                uint32_t any;
-                {
-                    const uint32_t need = mx > m_prev + 8.0f ? 1u : 0u;
-                    asm volatile(
-                        "{\n\t"
-                        ".reg .pred pin, pout;\n\t"
-                        "setp.ne.u32 pin, %1, 0;\n\t"
-                        "bar.red.or.pred pout, %2, 64, pin;\n\t"
-                        "selp.u32 %0, 1, 0, pout;\n\t"
-                        "}" : "=r"(any) : "r"(need), "r"(pair_bar) : "memory");
-                }
-                float alpha = 1.f;
-                if (any) {
-                    xch[(b * 2 + h) * 128 + row] = mx;
-                    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-                    const float joint = fmaxf(mx, xch[(b * 2 + (h ^ 1)) * 128 + row]);
-                    const float m_new = joint > m_prev + 8.0f ? joint : m_prev;
-                    alpha = m_prev == -INFINITY ? 0.f : fast_exp2(m_prev - m_new);      // 1 exactly if unchanged
-                    l *= alpha;
-                    m_ref = m_new;
-                }
-                // hand M(p) to the warps of pair p+1 (both of this pair's warps have read M(p-1): they met at the vote)
-                if (h == 0) {
-                    m_pub[b * 128 + row] = m_ref;
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(DEC + b * 4 + quad));
-                }
-                if (any) {
-                    if (p >= 1) {
-                        // O holds PV(0) .. PV(p-1) in the scale of M(p-1); PV(p) cannot start before this thread's P_FULL arrival
-                        mbar_wait(bar(PV_DONE + (b ^ 1)), ((p - 1) >> 1) & 1);
-                        tc_fence_after();
-#pragma unroll 1
-                        for (int c = 0; c < 4; ++c) {
-                            uint32_t ov[16];
-                            LS_TMEM_LD16(o_half + c * 16, ov);
-                            tmem_wait_ld();
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
-                            LS_TMEM_ST16(o_half + c * 16, ov);
-                        }
-                        tmem_wait_st();
-                    }
-                    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // xch is reused by the next exchange
-                }
-            } else {
-                uint32_t any;
-                {
-                    const uint32_t need = mx > m_ref + 8.0f ? 1u : 0u;   // lazy rescale threshold (2^8)
-                    asm volatile(
-                        "{\n\t"
-                        ".reg .pred pin, pout;\n\t"
-                        "setp.ne.u32 pin, %1, 0;\n\t"
-                        "bar.red.or.pred pout, %2, 64, pin;\n\t"
-                        "selp.u32 %0, 1, 0, pout;\n\t"
-                        "}" : "=r"(any) : "r"(need), "r"(pair_bar) : "memory");
-                }
-                if (any) {
-                    xch[(b * 2 + h) * 128 + row] = mx;
-                    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-                    const float joint = fmaxf(mx, xch[(b * 2 + (h ^ 1)) * 128 + row]);
-                    const float m_new = joint > m_ref + 8.0f ? joint : m_ref;
-                    const float alpha = m_ref == -INFINITY ? 0.f : fast_exp2(m_ref - m_new);
-                    l *= alpha;
-                    m_ref = m_new;
-                    if (it >= 1) {
-                        // The accumulator's previous PV is pair p-2.  It was issued after QK(p), so S_FULL(p) does not
-                        // certify it: wait for its own completion.  PV(p-4) is known complete (P(p-2) was only stored
-                        // after PV(p-3), and MMAs complete in order) and PV(p) cannot have run, so the parity is unambiguous.
-                        mbar_wait(bar(PV_DONE + b), (it - 1) & 1);
-                        tc_fence_after();
-    #pragma unroll 1
-                        for (int c = 0; c < 4; ++c) {
-                            uint32_t ov[16];
-                            LS_TMEM_LD16(o_half + c * 16, ov);
-                            tmem_wait_ld();
-    #pragma unroll
-                            for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
-                            LS_TMEM_ST16(o_half + c * 16, ov);
-                        }
-                        tmem_wait_st();
-                    }
-                    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-                }
+            uint32_t any;
+            {
+                const uint32_t need = mx > m_ref + 8.0f ? 1u : 0u;   // lazy rescale threshold (2^8)
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred pin, pout;\n\t"
+                    "setp.ne.u32 pin, %1, 0;\n\t"
+                    "bar.red.or.pred pout, %2, 64, pin;\n\t"
+                    "selp.u32 %0, 1, 0, pout;\n\t"
+                    "}" : "=r"(any) : "r"(need), "r"(pair_bar) : "memory");
             }
+            if (any) {
+                xch[(b * 2 + h) * 128 + row] = mx;
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                const float joint = fmaxf(mx, xch[(b * 2 + (h ^ 1)) * 128 + row]);
+                const float m_new = joint > m_ref + 8.0f ? joint : m_ref;
+                const float alpha = m_ref == -INFINITY ? 0.f : fast_exp2(m_ref - m_new);
+                l *= alpha;
+                m_ref = m_new;
+                if (it >= 1) {
+                    // The accumulator's previous PV is pair p-2.  It was issued after QK(p), so S_FULL(p) does not
+                    // certify it: wait for its own completion.  PV(p-4) is known complete (P(p-2) was only stored
+                    // after PV(p-3), and MMAs complete in order) and PV(p) cannot have run, so the parity is unambiguous.
+                    mbar_wait(bar(PV_DONE + b), (it - 1) & 1);
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t ov[16];
+                        LS_TMEM_LD16(o_half + c * 16, ov);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+                        LS_TMEM_ST16(o_half + c * 16, ov);
+                    }
+                    tmem_wait_st();
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            }
+        
             const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
             uint32_t pk[32];
             if (gi >= total_tiles) l += exp_regs<T, 0>(sv, pk, c2x2, pack2(-m_use, -m_use));
@@ -1320,86 +1247,44 @@ attn_tc1_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k,
         auto part_base = [&](int sl, int rp) { return (static_cast<size_t>(d.part_offset + sl) * d.n_kv_heads + kvh) * Rtot + rp; };
         float* stage = reinterpret_cast<float*>(smem);               // [128 rows][OUT_STRIDE]: the K ring is dead (every MMA has completed)
         asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (ONE_ACC) {
-            // One accumulator in the scale of the last pair's reference; the four threads of a row hold partial sums
-            // relative to the reference each of them used last (references only grow: the largest is the final one).
-            float* st_m = xch;                                       // [4 warpgroups][128]
-            float* st_l = xch + 4 * 128;                             // [4 warpgroups][128]
-            st_m[wgi * 128 + row] = m_ref;
-            st_l[wgi * 128 + row] = l;
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            float m = -INFINITY;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) m = fmaxf(m, st_m[w * 128 + row]);
-            float lt = 0.f;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const float lw = st_l[w * 128 + row], mw = st_m[w * 128 + row];
-                if (lw > 0.f) lt += lw * fast_exp2(mw - m);
+        float* st_m = xch;                                           // [2][128]
+        float* st_l = xch + 2 * 128;                                 // [2][2][128]
+        if (h == 0) st_m[b * 128 + row] = m_ref;
+        st_l[(b * 2 + h) * 128 + row] = l;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const float m0 = st_m[row], m1 = st_m[128 + row];
+        const float l0 = st_l[row] + st_l[128 + row], l1 = st_l[256 + row] + st_l[384 + row];
+        const float m = fmaxf(m0, m1);
+        const float a0 = l0 > 0.f ? fast_exp2(m0 - m) : 0.f, a1 = l1 > 0.f ? fast_exp2(m1 - m) : 0.f;
+        const float lt = l0 * a0 + l1 * a1;
+        const float inv = lt > 0.f ? 1.f / lt : 0.f;
+        const float w0 = a0 * inv, w1 = a1 * inv;
+        const bool live = n_pairs > 0;
+        const int rp = rp0 + row;
+        if (wgi == 0 && rp < R) {
+            d.part_lse[part_base(slot, rp)] = (live && inv > 0.f) ? (m + log2f(lt)) * 0.6931471805599453f : -INFINITY;
+            if (empty_slot >= 0) d.part_lse[part_base(empty_slot, rp)] = -INFINITY;
+        }
+        if (warp_valid) {                                        // warp-uniform (tcgen05.ld is warp-collective)
+            const int col = wgi * 32;
+            uint32_t o0[32], o1[32];
+            if (live) {
+                LS_TMEM_LD32(lane_addr + COL1_O + col, o0);
+                LS_TMEM_LD32(lane_addr + COL1_O + 128 + col, o1);
+                tmem_wait_ld();
             }
-            const float inv = lt > 0.f ? 1.f / lt : 0.f;
-            const bool live = n_pairs > 0;
-            const int rp = rp0 + row;
-            if (wgi == 0 && rp < R) {
-                d.part_lse[part_base(slot, rp)] = (live && inv > 0.f) ? (m + log2f(lt)) * 0.6931471805599453f : -INFINITY;
-                if (empty_slot >= 0) d.part_lse[part_base(empty_slot, rp)] = -INFINITY;
-            }
-            if (warp_valid) {
-                const int col = wgi * 32;
-                uint32_t o0[32];
-                if (live) {
-                    LS_TMEM_LD32(lane_addr + COL1_O + col, o0);
-                    tmem_wait_ld();
-                }
-                float* ps = stage + row * OUT_STRIDE + col;
+            float* ps = stage + row * OUT_STRIDE + col;
 #pragma unroll
-                for (int e = 0; e < 32; e += 4) {
-                    float x[4];
+            for (int e = 0; e < 32; e += 4) {
+                float x[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) x[u] = (live && inv > 0.f) ? __uint_as_float(o0[e + u]) * inv : 0.f;
-                    *reinterpret_cast<float4*>(ps + e) = make_float4(x[0], x[1], x[2], x[3]);
+                for (int u = 0; u < 4; ++u) {
+                    // an accumulator that never received a PV holds stale TMEM bits: select, do not multiply
+                    const float x0 = (live && w0 > 0.f) ? __uint_as_float(o0[e + u]) * w0 : 0.f;
+                    const float x1 = (live && w1 > 0.f) ? __uint_as_float(o1[e + u]) * w1 : 0.f;
+                    x[u] = x0 + x1;
                 }
-            }
-        } else {
-            float* st_m = xch;                                       // [2][128]
-            float* st_l = xch + 2 * 128;                             // [2][2][128]
-            if (h == 0) st_m[b * 128 + row] = m_ref;
-            st_l[(b * 2 + h) * 128 + row] = l;
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            const float m0 = st_m[row], m1 = st_m[128 + row];
-            const float l0 = st_l[row] + st_l[128 + row], l1 = st_l[256 + row] + st_l[384 + row];
-            const float m = fmaxf(m0, m1);
-            const float a0 = l0 > 0.f ? fast_exp2(m0 - m) : 0.f, a1 = l1 > 0.f ? fast_exp2(m1 - m) : 0.f;
-            const float lt = l0 * a0 + l1 * a1;
-            const float inv = lt > 0.f ? 1.f / lt : 0.f;
-            const float w0 = a0 * inv, w1 = a1 * inv;
-            const bool live = n_pairs > 0;
-            const int rp = rp0 + row;
-            if (wgi == 0 && rp < R) {
-                d.part_lse[part_base(slot, rp)] = (live && inv > 0.f) ? (m + log2f(lt)) * 0.6931471805599453f : -INFINITY;
-                if (empty_slot >= 0) d.part_lse[part_base(empty_slot, rp)] = -INFINITY;
-            }
-            if (warp_valid) {                                        // warp-uniform (tcgen05.ld is warp-collective)
-                const int col = wgi * 32;
-                uint32_t o0[32], o1[32];
-                if (live) {
-                    LS_TMEM_LD32(lane_addr + COL1_O + col, o0);
-                    LS_TMEM_LD32(lane_addr + COL1_O + 128 + col, o1);
-                    tmem_wait_ld();
-                }
-                float* ps = stage + row * OUT_STRIDE + col;
-#pragma unroll
-                for (int e = 0; e < 32; e += 4) {
-                    float x[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        // an accumulator that never received a PV holds stale TMEM bits: select, do not multiply
-                        const float x0 = (live && w0 > 0.f) ? __uint_as_float(o0[e + u]) * w0 : 0.f;
-                        const float x1 = (live && w1 > 0.f) ? __uint_as_float(o1[e + u]) * w1 : 0.f;
-                        x[u] = x0 + x1;
-                    }
-                    *reinterpret_cast<float4*>(ps + e) = make_float4(x[0], x[1], x[2], x[3]);
-                }
+                *reinterpret_cast<float4*>(ps + e) = make_float4(x[0], x[1], x[2], x[3]);
             }
         }
         asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -1504,13 +1389,13 @@ static int tc1_mode() {
     if (g_tc1_mode < 0) {
         const char* e = getenv("LONGSPEC_TC1");
         const int m = e ? atoi(e) : 1;
-        g_tc1_mode = m < 0 ? 0 : (m > 3 ? 3 : m);
+        g_tc1_mode = m < 0 ? 0 : (m > 2 ? 2 : m);
     }
     return g_tc1_mode;
 }
 extern "C" int ls_attn_tc1_mode(int mode) {
     const int prev = tc1_mode();
-    if (mode >= 0 && mode <= 3) g_tc1_mode = mode;
+    if (mode >= 0 && mode <= 2) g_tc1_mode = mode;
     return prev;
 }
 
@@ -1544,13 +1429,11 @@ static int launch_tc(const ls_attn_desc* d, int n_splits_tc, int fuse_remainder,
     if (nrs > NRL_MAX && mode1 > 0 && !(fuse & 2)) {
         const int gx = 3 * ((n_splits_tc + 1) / 2);
         const bool cluster = mode1 == 2 && gx % 2 == 0;
-        const int variant = mode1 == 3 ? 2 : (cluster ? 1 : 0);
-        static unsigned long long ok1[6] = {0, 0, 0, 0, 0, 0};
-        const int which = variant * 2 + (d->dtype == LS_F16 ? 0 : 1);
-        static const void* const fns[6] = {
-            reinterpret_cast<const void*>(attn_tc1_kernel<__half, 0>), reinterpret_cast<const void*>(attn_tc1_kernel<__nv_bfloat16, 0>),
-            reinterpret_cast<const void*>(attn_tc1_kernel<__half, 1>), reinterpret_cast<const void*>(attn_tc1_kernel<__nv_bfloat16, 1>),
-            reinterpret_cast<const void*>(attn_tc1_kernel<__half, 2>), reinterpret_cast<const void*>(attn_tc1_kernel<__nv_bfloat16, 2>)};
+        static unsigned long long ok1[4] = {0, 0, 0, 0};
+        const int which = (cluster ? 2 : 0) + (d->dtype == LS_F16 ? 0 : 1);
+        static const void* const fns[4] = {
+            reinterpret_cast<const void*>(attn_tc1_kernel<__half, false>), reinterpret_cast<const void*>(attn_tc1_kernel<__nv_bfloat16, false>),
+            reinterpret_cast<const void*>(attn_tc1_kernel<__half, true>), reinterpret_cast<const void*>(attn_tc1_kernel<__nv_bfloat16, true>)};
         const void* fn = fns[which];
         rc = ensure_dyn_smem(fn, one::SMEM1_BYTES, &ok1[which], "ls_attn_partial_tc (one row tile per CTA)");
         if (rc) return rc;
