@@ -1382,8 +1382,8 @@ static bool tc_can_fuse_combine(const ls_attn_desc* d, int n_splits_tc) {
 }
 
 // Which kernel serves calls with three row tiles: 0 = attn_tc_kernel (heavy / heavy / light trios), 1 = attn_tc1_kernel
-// (one row tile per CTA; measured fastest: default), 2 = attn_tc1_kernel as clusters of two with TMA multicast (less L2
-// traffic, but the lock-step of the pair costs more than it saves).  LONGSPEC_TC1 sets the initial value.
+// (one row tile per CTA; measured fastest: default), 2 = attn_tc1_kernel as clusters of two with TMA multicast (a third
+// less L2 -> SM traffic, same speed at 128k, but 3 us of cluster launch / barriers per call).  LONGSPEC_TC1 sets the initial value.
 static int g_tc1_mode = -1;
 static int tc1_mode() {
     if (g_tc1_mode < 0) {
