@@ -177,3 +177,43 @@ def test_tc_kernel_role_assignment_covers_every_tile_and_slot_once(nrs):
                     if c["rows"] == [2] and c["empty_slot"] >= 0:
                         heavy = [h for h in ctas if h["rows"] == [0, 1] and h["slot"] in (c["slot"], c["empty_slot"])]
                         assert all(abs(2 * len(h["tiles"]) - len(c["tiles"])) <= 1 for h in heavy)
+
+
+def _tc1_roles(n_slots, all_tiles):
+    """Host-side mirror of attn_tc1_kernel's role assignment (one row tile per CTA, three row tiles per call): trio g = the
+    key tiles of slots 2g, 2g+1; CTAs [0, 2T) = row tile bx & 1 of trio bx >> 1, CTAs [2T, 3T) = row tile 2."""
+    n_trios = (n_slots + 1) >> 1
+    per = (all_tiles + n_slots - 1) // n_slots
+    ctas = []
+    for bx in range(3 * n_trios):
+        light = bx >= 2 * n_trios
+        g = bx - 2 * n_trios if light else bx >> 1
+        rt = 2 if light else bx & 1
+        share0 = 2 * g
+        nshare = min(2, n_slots - share0)
+        lo, hi = min(share0 * per, all_tiles), min((share0 + nshare) * per, all_tiles)
+        ctas.append(dict(slot=share0, empty_slot=share0 + 1 if nshare == 2 else -1, row=rt, tiles=list(range(lo, hi)),
+                         cluster=bx >> 1, heavy=not light))
+    return ctas
+
+
+def test_tc1_kernel_role_assignment_covers_every_tile_and_slot_once():
+    """attn_tc1_kernel: every (key tile, row tile) has one CTA, every (slot, row tile) one writer; the two CTAs of a
+    multicast cluster (LONGSPEC_TC1=2: blockIdx.x pairs) are the row tiles 0 / 1 of ONE trio and walk the same tiles."""
+    for n_slots in range(1, 20):
+        for all_tiles in (0, 1, 2, 3, 7, 12, 13, 64, 1031):
+            ctas = _tc1_roles(n_slots, all_tiles)
+            seen, writers = {}, {}
+            for c in ctas:
+                writers[(c["slot"], c["row"])] = writers.get((c["slot"], c["row"]), 0) + 1
+                if c["empty_slot"] >= 0:
+                    writers[(c["empty_slot"], c["row"])] = writers.get((c["empty_slot"], c["row"]), 0) + 1
+                for t in c["tiles"]:
+                    seen[(t, c["row"])] = seen.get((t, c["row"]), 0) + 1
+            assert all(v == 1 for v in seen.values())
+            assert set(seen) == {(t, r) for t in range(all_tiles) for r in range(3)}
+            assert writers == {(s, r): 1 for s in range(n_slots) for r in range(3)}, (n_slots, all_tiles)
+            heavy = [c for c in ctas if c["heavy"]]
+            for a, b in zip(heavy[0::2], heavy[1::2]):
+                assert a["cluster"] == b["cluster"] and (a["row"], b["row"]) == (0, 1) and a["tiles"] == b["tiles"]
+            assert len({len(c["tiles"]) for c in ctas if c["slot"] == 0}) == 1      # a trio's three CTAs run the same number of pairs
