@@ -82,7 +82,8 @@ typedef struct ls_attn_desc {
     const int32_t* n_q_ptr;     /* device scalar */
     const uint64_t* tail_mask;  /* [q_rows][LS_MASK_WORDS] or NULL when n_tail == 0 */
     float* part_o;              /* workspace [n_parts_total][n_kv_heads][q_rows*group][128] fp32 */
-    float* part_lse;            /* workspace [n_parts_total][n_kv_heads][q_rows*group] fp32 */
+    float* part_lse;            /* workspace [n_parts_total][n_kv_heads][q_rows*group] fp32; -inf = this slot saw no key for the
+                                   row: its part_o row is then unspecified and never read by the merges */
     int32_t kv_len_bias;        /* added to *kv_len_ptr (may be negative) */
     int32_t q_rows;             /* allocated query rows (<= 256) */
     int32_t n_heads;

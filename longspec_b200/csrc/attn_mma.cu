@@ -371,7 +371,8 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const ls_attn_desc d,
 #pragma unroll 4
                 for (int k = 0; k < cnt; ++k) {
                     const float w = __shfl_sync(0xffffffffu, w_mine, k);
-                    const float4 v = *reinterpret_cast<const float4*>(base + k * stride * kD);
+                    // an empty slot (LSE = -inf) carries no O row: never read it (its memory may hold anything)
+                    const float4 v = w != 0.f ? *reinterpret_cast<const float4*>(base + k * stride * kD) : make_float4(0.f, 0.f, 0.f, 0.f);
                     acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
                     acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
                 }
@@ -447,7 +448,8 @@ __global__ void __launch_bounds__(256) attn_reduce_push_kernel(const ls_attn_des
 #pragma unroll 4
                     for (int k = 0; k < cnt; ++k) {
                         const float w = __shfl_sync(0xffffffffu, w_mine, k);
-                        const float4 v = *reinterpret_cast<const float4*>(base + k * stride * kD);
+                        // an empty slot (LSE = -inf) carries no O row: never read it (its memory may hold anything)
+                        const float4 v = w != 0.f ? *reinterpret_cast<const float4*>(base + k * stride * kD) : make_float4(0.f, 0.f, 0.f, 0.f);
                         acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
                         acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
                     }

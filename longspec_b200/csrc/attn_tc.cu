@@ -813,8 +813,6 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
                 if (rp >= R) break;                                  // rows ascend with r: nothing live behind
                 const float4 v = *reinterpret_cast<const float4*>(stage + r * OUT_STRIDE + lane * 4);
                 *reinterpret_cast<float4*>(d.part_o + part_base(slot, rp) * 128 + lane * 4) = v;
-                if (empty_slot >= 0)
-                    *reinterpret_cast<float4*>(d.part_o + part_base(empty_slot, rp) * 128 + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         // ---- fused combine (ls_attn_desc::fuse_sync): the CTAs of this kv head meet at a counter barrier, then share
@@ -853,7 +851,8 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
 #pragma unroll 4
                         for (int k = 0; k < n_slots; ++k) {
                             const float w = __shfl_sync(0xffffffffu, w_mine, k);
-                            const float4 v = __ldcg(reinterpret_cast<const float4*>(base + k * pstride * 128));
+                            const float4 v = w != 0.f ? __ldcg(reinterpret_cast<const float4*>(base + k * pstride * 128))
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);      // empty slots carry no O row
                             acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
                             acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
                         }
@@ -1295,8 +1294,6 @@ attn_tc1_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k,
                 if (rp >= R) break;
                 const float4 v = *reinterpret_cast<const float4*>(stage + r * OUT_STRIDE + lane * 4);
                 *reinterpret_cast<float4*>(d.part_o + part_base(slot, rp) * 128 + lane * 4) = v;
-                if (empty_slot >= 0)
-                    *reinterpret_cast<float4*>(d.part_o + part_base(empty_slot, rp) * 128 + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         tc_fence_before();
