@@ -1015,24 +1015,33 @@ attn_tc1_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k,
     // one ring of STAGES1 tiles (K or V): executed by a whole converged warp, one elected lane issues
     auto tma_ring = [&](int full0, int empty0, int off, const CUtensorMap* map) {
         int s = 0, ph = 0;
-        for (int j = 0; j < n_pairs; ++j) {
-            const int gi = tile_lo + j;
-            const int tok = gi >= total_tiles ? sp_tiles[gi - total_tiles].tok : gi * BN;
-            const int page = __ldg(d.page_table + (tok >> 7));
-            const int row = (page * d.n_kv_heads + kvh) * LS_PAGE + (tok & (LS_PAGE - 1));
-            mbar_wait(bar(empty0 + s), ph ^ 1);
-            if (elect_one()) {
-                const uint32_t dst = sbase + off + s * TILE_BYTES;
-                mbar_expect_tx(bar(full0 + s), TILE_BYTES);
-                if (mc) {
-                    tma_load_2d_mc(dst + cta_rank * 16384, map, 64 * cta_rank, row, bar(full0 + s), 3);
-                } else {
-                    tma_load_2d(dst, map, 0, row, bar(full0 + s));
-                    tma_load_2d(dst + 16384, map, 64, row, bar(full0 + s));
-                }
+        for (int j0 = 0; j0 < n_pairs; j0 += 32) {
+            // the page-table lookups of the next 32 tiles in one round trip (one per lane) instead of one dependent
+            // global load in front of every TMA request
+            int row_l = 0;
+            if (j0 + lane < n_pairs) {
+                const int gi = tile_lo + j0 + lane;
+                const int tok = gi >= total_tiles ? sp_tiles[gi - total_tiles].tok : gi * BN;
+                const int page = __ldg(d.page_table + (tok >> 7));
+                row_l = (page * d.n_kv_heads + kvh) * LS_PAGE + (tok & (LS_PAGE - 1));
             }
-            __syncwarp();
-            if (++s == STAGES1) { s = 0; ph ^= 1; }
+            const int cnt = min(32, n_pairs - j0);
+            for (int k = 0; k < cnt; ++k) {
+                const int row = __shfl_sync(0xffffffffu, row_l, k);
+                mbar_wait(bar(empty0 + s), ph ^ 1);
+                if (elect_one()) {
+                    const uint32_t dst = sbase + off + s * TILE_BYTES;
+                    mbar_expect_tx(bar(full0 + s), TILE_BYTES);
+                    if (mc) {
+                        tma_load_2d_mc(dst + cta_rank * 16384, map, 64 * cta_rank, row, bar(full0 + s), 3);
+                    } else {
+                        tma_load_2d(dst, map, 0, row, bar(full0 + s));
+                        tma_load_2d(dst + 16384, map, 64, row, bar(full0 + s));
+                    }
+                }
+                __syncwarp();
+                if (++s == STAGES1) { s = 0; ph ^= 1; }
+            }
         }
     };
 
