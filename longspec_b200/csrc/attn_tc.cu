@@ -891,9 +891,9 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
 //   TMEM (512 columns) = O accumulators 2 x 128 | S 128 | P 64 | Q 64
 //
 //   * Q lives in TMEM (written once by the softmax warps with tcgen05.st): QK^T is a TS MMA that reads only the 4 KB K
-//     slice from shared memory per K step (8 KB with Q in shared memory: 80-82 instead of 57 cycles per MMA).
-//   * S is released as soon as its 128 x 128 scores sit in registers (S_FREE) and P has columns of its own, so QK(p+2)
-//     runs while pair p is still in softmax.  Issue order  QK(0) QK(1) | QK(2) PV(0) | QK(3) PV(1) | ...
+//     slice from shared memory per K step (8 KB with Q in shared memory), and Q needs no staging in shared memory.
+//   * S is released as soon as its 128 x 128 scores sit in registers (S_FREE) and P has columns of its own, so QK(p+1)
+//     and QK(p+2) run while pair p is still in softmax: the S -> softmax -> P -> PV chain no longer gates QK^T.
 //     P(p) is stored only once PV(p-1) has drained the P columns (PV_DONE) - the exponentials are already in registers.
 //   * Pairs alternate between the two accumulators (= softmax warpgroup pairs b = p & 1), each with its own reference
 //     maxima, exactly like the single-row-tile mode above; the epilogue merges the two partial states.
@@ -907,8 +907,9 @@ attn_tc_kernel(const ls_attn_desc d, const __grid_constant__ CUtensorMap map_k, 
 // tile of its trio, so with CLUSTER the CTAs of row tiles 0 and 1 form a cluster of two (one TPC): each loads one
 // 64-element half of every tile and TMA-multicasts it into both shared memories; a stage is free again when BOTH
 // CTAs' MMAs have released it (multicast tcgen05.commit onto both EMPTY barriers, count 2).  The row-tile-2 CTAs are
-// clustered in twos as well (the launch attribute is grid-wide) but run independently.  L2 -> SM traffic stays at twice
-// the algorithmic bytes, as before.
+// clustered in twos as well (the launch attribute is grid-wide) but run independently.  L2 -> SM traffic is then twice
+// the algorithmic bytes as in the trio kernel (three times without clusters - L2 runs at 28 % of its peak, so the default
+// is the plain launch: profiles/r02b_attn_tc1_ab.txt).
 namespace one {
 constexpr int STAGES1 = 3;
 constexpr int OFF_K1 = 0;
