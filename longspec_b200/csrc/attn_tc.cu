@@ -1,5 +1,9 @@
 // tcgen05 / TMA / TMEM split-KV attention over the paged prefix + the tree-masked tail (ls_attn_partial).
 //
+// Two kernels share the helpers of this file: attn_tc_kernel (described here; calls with up to two row tiles, and the
+// heavy / heavy / light trios that served three-row-tile calls in round 2a) and attn_tc1_kernel (further down: one row
+// tile per CTA, the default for three-row-tile calls - ls_attn_tc1_mode / LONGSPEC_TC1).
+//
 // Work unit: one CTA = (kv head, a share of the 128-key tiles, up to TWO row tiles of 128 packed query rows),
 // a packed row being r = token * G + head-in-group, so a K/V tile serves the whole GQA group and candidate tree.
 //
